@@ -1,0 +1,88 @@
+/* metaworld_b200.h -- C ABI of the batched Meta-World step engine (libmwb200.so).
+ *
+ * The reference has no FFI of its own: its hot path is the Python protocol
+ * gymnasium.vector.VectorEnv.step/reset over SawyerXYZEnv (metaworld/__init__.py:491-509,
+ * metaworld/sawyer_xyz_env.py:580-682) calling MuJoCo's C library.  Each entry point below
+ * names the reference call it stands in for.  Plain pointers and sizes only; pointers marked
+ * DEV are device pointers owned by the caller (e.g. torch tensors), everything else is host
+ * memory.  All functions return 0 on success, a negative mw_status otherwise; the failing call's
+ * message is available from mw_last_error().  Calls taking a stream are asynchronous on it.
+ */
+#ifndef METAWORLD_B200_H
+#define METAWORLD_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mw_engine mw_engine;
+
+enum mw_status { MW_OK = 0, MW_ERR_CUDA = -1, MW_ERR_ARG = -2, MW_ERR_STATE = -3 };
+
+/* sizes of the blobs the host code must pass (layout generated from metaworld_b200/lower.py) */
+int mw_sizeof_model(void);
+int mw_sizeof_taskconst(void);
+int mw_sizeof_envstate(void);   /* 512 bytes */
+int mw_sizeof_snapshot(void);   /* 768 bytes */
+const char* mw_last_error(void);
+const char* mw_build_info(void); /* "real=float maxcon=24 ..." */
+
+/* Construction: what MujocoEnv.__init__ -> MjModel.from_xml_path does per sub-env
+ * (metaworld/sawyer_xyz_env.py:53-63), for n_models distinct (model, task) slots.
+ *   models      : n_models consecutive MwModel blobs
+ *   taskconsts  : n_models consecutive MwTaskConst blobs
+ *   meshverts   : per model, hull vertices float[3*nmeshvert[i]] (may be NULL when 0)            */
+int mw_create(mw_engine** out, int device, int n_models, const void* models, const void* taskconsts,
+              const float* const* meshverts, const int* nmeshvert);
+void mw_destroy(mw_engine*);
+
+/* Environment table: env i uses model slot env_model[i]  (make_mt_envs / make_ml_envs building the
+ * sub-env list, metaworld/__init__.py:460-604).  Allocates the persistent per-env state.          */
+int mw_set_envs(mw_engine*, int n_envs, const int* env_model);
+
+/* Episode-start snapshots.  The reference's reset() = reset_model, mj_resetData, reset_model
+ * (2 x 50 x 5 mj_step, metaworld/sawyer_xyz_env.py:664-695) is a pure function of (task, rand_vec,
+ * partially_observable) because tasks freeze rand_vec (set_task, :298-318); it is evaluated once per
+ * distinct goal by the same device physics and cached.  Appends n snapshots, returns their ids.   */
+int mw_build_snapshots(mw_engine*, int n, const int* model_idx, const float* rand_vec /*[n,6]*/,
+                       const unsigned char* partially_observable, int* snapshot_ids_out);
+int mw_num_snapshots(const mw_engine*);
+/* copy snapshot records to the host (tests / checkpointing): out = n * mw_sizeof_snapshot() bytes */
+int mw_get_snapshots(mw_engine*, int first, int n, void* out);
+
+/* VectorEnv.reset (per-env SawyerXYZEnv.reset with the task chosen by the task-select wrapper,
+ * metaworld/wrappers.py:116-119): env_ids[k] (NULL = all envs in order) starts from snapshot_ids[k].
+ * obs: DEV float [n, obs_stride] (first 39 columns written).                                        */
+int mw_reset(mw_engine*, int n, const int* env_ids /*DEV or NULL*/, const int* snapshot_ids /*DEV*/,
+             float* obs /*DEV*/, int obs_stride, void* stream);
+
+/* VectorEnv.step with SAME_STEP autoreset (metaworld/__init__.py:465,491-509 ->
+ * SawyerXYZEnv.step, metaworld/sawyer_xyz_env.py:580-642 + TimeLimit + AutoTerminateOnSuccessWrapper,
+ * metaworld/wrappers.py:207-230).  All arrays DEV, n_envs rows:
+ *   actions [n,4] f32; obs [n,obs_stride] f32 (39 written); reward [n] f32; terminated/truncated [n] u8;
+ *   info [n,7] f32 = success, near_object, grasp_success, grasp_reward, in_place_reward, obj_to_target,
+ *   unscaled_reward; final_obs [n,obs_stride] / final_info [n,8] (7 infos + episode return) are written
+ *   only for rows whose episode ended in this call (terminated|truncated), which then restart from
+ *   next_snapshot[i] (or, when next_snapshot is NULL, from a snapshot drawn on the device from the env's
+ *   own goal set, see mw_set_goal_sets).                                                             */
+int mw_step(mw_engine*, const float* actions, float* obs, int obs_stride, float* reward,
+            unsigned char* terminated, unsigned char* truncated, float* info, float* final_obs,
+            float* final_info, const int* next_snapshot, void* stream);
+
+/* options: max_episode_steps (TimeLimit), terminate_on_success (0/1), device sampler seed */
+int mw_set_options(mw_engine*, int max_episode_steps, int terminate_on_success, unsigned long long seed);
+/* per-env contiguous range of snapshot ids [first, first+count) used by the device-side task sampler */
+int mw_set_goal_sets(mw_engine*, const int* first /*host [n_envs]*/, const int* count /*host [n_envs]*/);
+
+/* raw state access (tests, checkpoint/resume incl. physics state): n_envs * 512 bytes */
+int mw_get_state(mw_engine*, void* out_host);
+int mw_set_state(mw_engine*, const void* in_host);
+/* debug: run nstep raw physics substeps (mj_step) on every env with fixed ctrl, no reward/obs */
+int mw_debug_substeps(mw_engine*, int nstep, const float* ctrl2 /*host [2]*/, void* stream);
+/* counters accumulated since the last call: [0] kernel launches, [1] env steps, [2] contacts dropped,
+ * [3] solver iterations (sum over forward passes), [4] forward passes */
+int mw_get_counters(mw_engine*, unsigned long long* out5);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

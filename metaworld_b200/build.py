@@ -1,0 +1,58 @@
+"""Builds libmwb200.so (the CUDA engine, C ABI in include/metaworld_b200.h) in-tree with nvcc for sm_100a."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+SO = os.path.join(_HERE, "libmwb200.so")
+SOURCES = ["mw_engine.cu"]
+HEADERS = ["mw_math.cuh", "mw_collide.cuh", "mw_physics.cuh", "mw_tasks.cuh", "mw_tasks_gen.cuh"]
+
+
+def write_header():
+    from . import lower
+
+    path = os.path.join(CSRC, "mw_model.h")
+    txt = lower.emit_header()
+    if not os.path.exists(path) or open(path).read() != txt:
+        with open(path, "w") as f:
+            f.write(txt)
+    return path
+
+
+def needs_build():
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS + ["mw_model.h"]] + [os.path.join(_HERE, "lower.py"),
+            os.path.join(_HERE, "..", "include", "metaworld_b200.h")]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False, real_double=False, extra=()):
+    write_header()
+    if not force and not needs_build():
+        return SO
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math" if False else "-DMW_NO_FASTMATH",
+           "-Xcompiler", "-fPIC", "-shared", "-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+    if real_double:
+        cmd.insert(1, "-DMW_REAL_DOUBLE")
+    if verbose:
+        cmd[1:1] = ["-Xptxas", "-v"]
+    cmd[1:1] = list(extra)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed")
+    if verbose:
+        print(r.stdout + r.stderr)
+    return SO
+
+
+if __name__ == "__main__":
+    build(force=True, verbose="-v" in sys.argv, real_double="--double" in sys.argv)
+    print(SO)

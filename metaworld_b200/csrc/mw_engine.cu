@@ -1,0 +1,494 @@
+// libmwb200: batched Meta-World step engine for B200 (sm_100a).  C ABI: include/metaworld_b200.h.
+//
+// One warp = one environment for a whole env step: 5 x (forward dynamics + semi-implicit Euler), one more
+// forward pass, observation, reward/info, time-limit / success termination and SAME_STEP autoreset, with the
+// per-env state making a single 512-byte round trip to HBM (coalesced 128-bit loads/stores).  One CTA = 8 warps
+// that share one task model; the ~10 KB model blob is staged into shared memory with a TMA bulk copy
+// (cp.async.bulk + mbarrier).  There is no CPU fallback: every entry point launches CUDA kernels or fails.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/metaworld_b200.h"
+#include "mw_tasks.cuh"
+
+#define WARPS_PER_BLOCK 8
+#define BLOCK_THREADS (WARPS_PER_BLOCK * 32)
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return fail(MW_ERR_CUDA, std::string(#x ": ") + cudaGetErrorString(e_)); } while (0)
+
+struct EngineDev {
+  const unsigned char* models; int model_stride;     // MwModel blobs (stride multiple of 16)
+  const MwTaskConst* taskconsts;
+  const float* const* meshverts;                     // [n_models] device pointers
+  MwEnvState* state; MwSnapshot* snaps;
+  const int* goal_first; const int* goal_count;      // device sampler ranges (may be NULL)
+  int* diag;                                         // [n_envs][2]: contacts dropped, solver iterations
+  int n_envs, max_steps, terminate_on_success; unsigned long long seed;
+};
+
+// ---------------------------------------------------------------- shared memory carve-up
+struct BlockShared {
+  alignas(16) unsigned char model[(sizeof(MwModel) + 15) / 16 * 16];
+  MwTaskConst tc;
+  alignas(8) unsigned long long bar;
+};
+struct WarpShared {
+  WarpScratch w;
+  alignas(16) MwEnvState es;
+  float obs[40]; float info[8];
+};
+static size_t smem_bytes() { return sizeof(BlockShared) + WARPS_PER_BLOCK * sizeof(WarpShared) + 16; }
+
+DEV unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+// TMA bulk copy global -> shared with mbarrier completion (SASS: UBLKCP / SYNCS)
+DEV void stage_model(BlockShared* bs, const unsigned char* src, unsigned bytes, const MwTaskConst* tc_src) {
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bs->bar)));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bs->bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(bs->model)), "l"(src), "r"(bytes), "r"(smem_u32(&bs->bar)) : "memory");
+  }
+  // the small task-constant record rides along with ordinary loads
+  for (int i = threadIdx.x; i < (int)(sizeof(MwTaskConst) / 4); i += blockDim.x) ((int*)&bs->tc)[i] = ((const int*)tc_src)[i];
+  unsigned ok = 0;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(smem_u32(&bs->bar)), "r"(0u) : "memory");
+  } while (!ok);
+  __syncthreads();
+}
+
+struct Eng { const MwModel* m; const float* meshvert; };
+__device__ void eng_forward(const TaskCtx& c, int lane) { mw_forward(c.m, c.meshvert, c.w, lane); }
+__device__ void eng_sim(const TaskCtx& c, int nstep, int lane) {
+  for (int s = 0; s < nstep; s++) { mw_forward(c.m, c.meshvert, c.w, lane); mw_euler(c.m, c.w, lane); }
+}
+
+// ---------------------------------------------------------------- state <-> scratch
+DEV void load_env(WarpShared* ws, const MwEnvState* src, int lane) {
+  ((float4*)&ws->es)[lane] = ((const float4*)src)[lane];     // 32 lanes x 16 B = the whole 512 B record
+  SYNCW();
+  WarpScratch* w = &ws->w;
+  if (lane < MW_MAXNQ) w->qpos[lane] = ws->es.qpos[lane];
+  if (lane < MW_MAXDOF) { w->qvel[lane] = ws->es.qvel[lane]; w->warm[lane] = ws->es.warm[lane]; }
+  if (lane < 3) { w->mocap_pos[lane] = ws->es.mocap_pos[lane]; w->shift[lane] = ws->es.shift[lane]; }
+  if (lane == 0) { w->mocap_quat[0] = 1; w->mocap_quat[1] = 0; w->mocap_quat[2] = 1; w->mocap_quat[3] = 0; w->ctrl[0] = w->ctrl[1] = 0; }
+  SYNCW();
+}
+DEV void store_env(WarpShared* ws, MwEnvState* dst, int lane) {
+  WarpScratch* w = &ws->w;
+  if (lane < MW_MAXNQ) ws->es.qpos[lane] = (float)w->qpos[lane];
+  if (lane < MW_MAXDOF) { ws->es.qvel[lane] = (float)w->qvel[lane]; ws->es.warm[lane] = (float)w->warm[lane]; }
+  if (lane < 3) { ws->es.mocap_pos[lane] = (float)w->mocap_pos[lane]; ws->es.shift[lane] = (float)w->shift[lane]; }
+  SYNCW();
+  ((float4*)dst)[lane] = ((const float4*)&ws->es)[lane];
+}
+
+// observation assembly (sawyer_xyz_env.py:475-527 + clip :623-628); lane 0
+DEV void make_obs(const TaskCtx& c, float* obs) {
+  real cur[18];
+  mw_frame_pos(c.m, c.w, F_HAND, cur);
+  real a[3], b[3]; mw_frame_pos(c.m, c.w, F_RCLAW, a); mw_frame_pos(c.m, c.w, F_LCLAW, b);
+  cur[3] = fmin(fmax(dist3(a, b) / (real)0.1, (real)0), (real)1);
+  task_obs_objects(c, cur + 4);
+  const real hlo[3] = {(real)-0.525, (real)0.348, (real)-0.0525}, hhi[3] = {(real)0.525, (real)1.025, (real)0.7};
+  for (int i = 0; i < 18; i++) {
+    real v = cur[i], pv = c.s->prev_obs[i];
+    if (i < 3) { v = fmin(fmax(v, hlo[i]), hhi[i]); pv = fmin(fmax(pv, hlo[i]), hhi[i]); }
+    if (i == 3) { v = fmin(fmax(v, (real)-1), (real)1); pv = fmin(fmax(pv, (real)-1), (real)1); }
+    obs[i] = (float)v; obs[18 + i] = (float)pv;
+    c.s->prev_obs[i] = (float)cur[i];
+  }
+  for (int i = 0; i < 3; i++) {
+    real g = c.s->partially_observable != 0.f ? (real)0 : fmin(fmax((real)c.s->target[i], (real)c.tc->goal_lo[i]), (real)c.tc->goal_hi[i]);
+    obs[36 + i] = (float)g;
+  }
+}
+
+DEV unsigned long long mix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull; return x ^ (x >> 31);
+}
+
+// ---------------------------------------------------------------- kernels
+__global__ void __launch_bounds__(BLOCK_THREADS, 1)
+k_step(EngineDev e, const int* __restrict__ block_model, const int* __restrict__ block_start, const int* __restrict__ block_count,
+       const int* __restrict__ perm, const float* __restrict__ actions, float* __restrict__ obs_out, int obs_stride,
+       float* __restrict__ reward, unsigned char* __restrict__ terminated, unsigned char* __restrict__ truncated,
+       float* __restrict__ info_out, float* __restrict__ final_obs, float* __restrict__ final_info, const int* __restrict__ next_snapshot) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  BlockShared* bs = (BlockShared*)smem;
+  WarpShared* wsa = (WarpShared*)(smem + sizeof(BlockShared));
+  const int mi = block_model[blockIdx.x];
+  stage_model(bs, e.models + (size_t)mi * e.model_stride, (unsigned)sizeof(bs->model), e.taskconsts + mi);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= block_count[blockIdx.x]) return;
+  const int env = perm[block_start[blockIdx.x] + warp];
+  WarpShared* ws = wsa + warp;
+  WarpScratch* w = &ws->w;
+  const MwModel* m = (const MwModel*)bs->model;
+  load_env(ws, e.state + env, lane);
+  real act[4];
+  for (int i = 0; i < 4; i++) act[i] = fmin(fmax((real)actions[4 * env + i], (real)-1), (real)1);
+  TaskCtx c; c.m = m; c.tc = &bs->tc; c.w = w; c.s = &ws->es; c.action = act; c.meshvert = e.meshverts[mi];
+  // set_xyz_action (sawyer_xyz_env.py:320-336) + ctrl = [a3, -a3] (:595)
+  if (lane < 3) w->mocap_pos[lane] = fmin(fmax(w->mocap_pos[lane] + act[lane] * (real)0.01, (real)bs->tc.mocap_lo[lane]), (real)bs->tc.mocap_hi[lane]);
+  if (lane == 0) { w->ctrl[0] = (real)actions[4 * env + 3]; w->ctrl[1] = -(real)actions[4 * env + 3]; }
+  SYNCW();
+  int iters = 0, dropped = 0;
+  for (int s = 0; s < 5; s++) { mw_forward(m, c.meshvert, w, lane); iters += w->solver_iter; dropped += w->ncon_dropped; mw_euler(m, w, lane); }
+  mw_forward(m, c.meshvert, w, lane);
+  iters += w->solver_iter; dropped += w->ncon_dropped;
+  bool done = false;
+  if (lane == 0) {
+    ws->es.path_len += 1.f;
+    make_obs(c, ws->obs);
+    real obsr[39]; for (int i = 0; i < 39; i++) obsr[i] = ws->obs[i];
+    real rew, inf[INFO_N];
+    real raw_act[4]; for (int i = 0; i < 4; i++) raw_act[i] = actions[4 * env + i];
+    c.action = raw_act;
+    task_reward(c, obsr, &rew, inf);
+    for (int i = 0; i < INFO_N; i++) ws->info[i] = (float)inf[i];
+    ws->es.ep_return += (float)rew;
+    bool trunc = ws->es.path_len >= (float)e.max_steps;
+    bool term = e.terminate_on_success && inf[INFO_SUCCESS] == (real)1;
+    reward[env] = (float)rew; terminated[env] = term; truncated[env] = trunc;
+    ws->info[7] = (term || trunc) ? 1.f : 0.f;
+    e.diag[2 * env] += dropped; e.diag[2 * env + 1] += iters;
+  }
+  SYNCW();
+  done = ws->info[7] != 0.f;
+  if (lane < INFO_N) info_out[(size_t)env * INFO_N + lane] = ws->info[lane];
+  if (!done) {
+    for (int i = lane; i < 39; i += 32) obs_out[(size_t)env * obs_stride + i] = ws->obs[i];
+    store_env(ws, e.state + env, lane);
+  } else {
+    // SAME_STEP autoreset: report the terminal transition, restart from a cached episode-start snapshot
+    if (final_obs) for (int i = lane; i < 39; i += 32) final_obs[(size_t)env * obs_stride + i] = ws->obs[i];
+    if (final_info) { if (lane < INFO_N) final_info[(size_t)env * 8 + lane] = ws->info[lane]; if (lane == 7) final_info[(size_t)env * 8 + 7] = ws->es.ep_return; }
+    int snap;
+    if (next_snapshot) snap = next_snapshot[env];
+    else {
+      unsigned long long h = mix64(e.seed ^ mix64(((unsigned long long)env << 32) | (unsigned)(int)ws->es.episode));
+      snap = e.goal_first[env] + (int)(h % (unsigned long long)e.goal_count[env]);
+    }
+    float episode = ws->es.episode + 1.f;
+    const MwSnapshot* sp = e.snaps + snap;
+    float4 v = ((const float4*)&sp->st)[lane];
+    SYNCW();
+    ((float4*)&ws->es)[lane] = v;
+    SYNCW();
+    if (lane == 0) { ws->es.episode = episode; ws->es.snapshot = (float)snap; ws->es.ep_return = 0.f; ws->es.path_len = 0.f; }
+    SYNCW();
+    ((float4*)(e.state + env))[lane] = ((const float4*)&ws->es)[lane];
+    for (int i = lane; i < 39; i += 32) obs_out[(size_t)env * obs_stride + i] = sp->obs[i];
+  }
+}
+
+// builds episode-start snapshots: exact reset() sequence of the reference (reset_model, mj_resetData, reset_model)
+__global__ void __launch_bounds__(BLOCK_THREADS, 1)
+k_snapshot(EngineDev e, const int* __restrict__ block_model, const int* __restrict__ block_start, const int* __restrict__ block_count,
+           const int* __restrict__ perm, const float* __restrict__ rand_vec, const unsigned char* __restrict__ partial, int snap_base) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  BlockShared* bs = (BlockShared*)smem;
+  WarpShared* wsa = (WarpShared*)(smem + sizeof(BlockShared));
+  const int mi = block_model[blockIdx.x];
+  stage_model(bs, e.models + (size_t)mi * e.model_stride, (unsigned)sizeof(bs->model), e.taskconsts + mi);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= block_count[blockIdx.x]) return;
+  const int item = perm[block_start[blockIdx.x] + warp];
+  WarpShared* ws = wsa + warp;
+  WarpScratch* w = &ws->w;
+  const MwModel* m = (const MwModel*)bs->model;
+  const float* rv = rand_vec + 6 * item;
+  real act[4] = {0, 0, 0, 0};
+  TaskCtx c; c.m = m; c.tc = &bs->tc; c.w = w; c.s = &ws->es; c.action = act; c.meshvert = e.meshverts[mi];
+  for (int i = lane; i < 128; i += 32) ((float*)&ws->es)[i] = 0.f;
+  if (lane < 3) w->shift[lane] = 0;
+  SYNCW();
+  for (int pass = 0; pass < 2; pass++) {
+    if (pass == 1 || true) {
+      // mj_resetData (pass 0: a freshly constructed env is in the same state)
+      if (lane < MW_MAXNQ) w->qpos[lane] = lane < m->nq ? (real)m->qpos0[lane] : (real)0;
+      if (lane < MW_MAXDOF) { w->qvel[lane] = 0; w->warm[lane] = 0; }
+      if (lane < 3) w->mocap_pos[lane] = m->mocap_pos0[lane];
+      if (lane < 4) w->mocap_quat[lane] = m->mocap_quat0[lane];
+      if (lane < 2) w->ctrl[lane] = 0;
+      SYNCW();
+    }
+    // _reset_hand (sawyer_xyz_env.py:684-695)
+    for (int k = 0; k < 50; k++) {
+      if (lane < 3) w->mocap_pos[lane] = bs->tc.hand_init[lane];
+      if (lane == 0) { w->mocap_quat[0] = 1; w->mocap_quat[1] = 0; w->mocap_quat[2] = 1; w->mocap_quat[3] = 0; w->ctrl[0] = -1; w->ctrl[1] = 1; }
+      SYNCW();
+      eng_sim(c, 5, lane);
+    }
+    if (lane == 0) { real t[3]; tcp_center(c, t); for (int i = 0; i < 3; i++) ws->es.init_tcp[i] = (float)t[i]; }
+    SYNCW();
+    task_reset_model(c, rv, lane);
+    SYNCW();
+  }
+  if (lane == 0) {
+    ws->es.partially_observable = partial[item] ? 1.f : 0.f;
+    make_obs(c, ws->obs);                              // _get_obs() of pass 2
+    for (int i = 0; i < 18; i++) { ws->obs[18 + i] = ws->obs[i]; }   // reset(): obs[18:36] = obs[:18]  (:679-680)
+    ws->es.path_len = 0.f; ws->es.episode = 0.f; ws->es.ep_return = 0.f; ws->es.snapshot = (float)(snap_base + item);
+  }
+  SYNCW();
+  if (lane < 3) ws->es.shift[lane] = (float)w->shift[lane];
+  SYNCW();
+  MwSnapshot* sp = e.snaps + snap_base + item;
+  store_env(ws, &sp->st, lane);
+  for (int i = lane; i < 39; i += 32) sp->obs[i] = ws->obs[i];
+}
+
+__global__ void k_reset(EngineDev e, int n, const int* __restrict__ env_ids, const int* __restrict__ snapshot_ids,
+                        float* __restrict__ obs, int obs_stride) {
+  int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= n) return;
+  int env = env_ids ? env_ids[gw] : gw;
+  const MwSnapshot* sp = e.snaps + snapshot_ids[gw];
+  float4 v = ((const float4*)&sp->st)[lane];
+  ((float4*)(e.state + env))[lane] = v;
+  if (lane == 0) e.state[env].snapshot = (float)snapshot_ids[gw];
+  for (int i = lane; i < 39; i += 32) obs[(size_t)gw * obs_stride + i] = sp->obs[i];
+}
+
+__global__ void __launch_bounds__(BLOCK_THREADS, 1)
+k_substeps(EngineDev e, const int* __restrict__ block_model, const int* __restrict__ block_start, const int* __restrict__ block_count,
+           const int* __restrict__ perm, int nstep, float c0, float c1) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  BlockShared* bs = (BlockShared*)smem;
+  WarpShared* wsa = (WarpShared*)(smem + sizeof(BlockShared));
+  const int mi = block_model[blockIdx.x];
+  stage_model(bs, e.models + (size_t)mi * e.model_stride, (unsigned)sizeof(bs->model), e.taskconsts + mi);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= block_count[blockIdx.x]) return;
+  const int env = perm[block_start[blockIdx.x] + warp];
+  WarpShared* ws = wsa + warp;
+  const MwModel* m = (const MwModel*)bs->model;
+  load_env(ws, e.state + env, lane);
+  if (lane == 0) { ws->w.ctrl[0] = c0; ws->w.ctrl[1] = c1; }
+  SYNCW();
+  for (int s = 0; s < nstep; s++) { mw_forward(m, e.meshverts[mi], &ws->w, lane); mw_euler(m, &ws->w, lane); }
+  store_env(ws, e.state + env, lane);
+}
+
+// ---------------------------------------------------------------- host side
+struct mw_engine {
+  int device = 0, n_models = 0, n_envs = 0, model_stride = 0;
+  unsigned char* d_models = nullptr; MwTaskConst* d_tc = nullptr; float** d_meshptrs = nullptr;
+  std::vector<float*> meshbufs;
+  MwEnvState* d_state = nullptr; MwSnapshot* d_snaps = nullptr; int snap_cap = 0, n_snaps = 0;
+  int *d_goal_first = nullptr, *d_goal_count = nullptr, *d_diag = nullptr;
+  // env block table
+  int n_blocks = 0; int *d_block_model = nullptr, *d_block_start = nullptr, *d_block_count = nullptr, *d_perm = nullptr;
+  int max_steps = 500, terminate_on_success = 0; unsigned long long seed = 0;
+  unsigned long long launches = 0, env_steps = 0;
+  EngineDev dev() const {
+    EngineDev e; e.models = d_models; e.model_stride = model_stride; e.taskconsts = d_tc; e.meshverts = d_meshptrs;
+    e.state = d_state; e.snaps = d_snaps; e.goal_first = d_goal_first; e.goal_count = d_goal_count; e.diag = d_diag;
+    e.n_envs = n_envs; e.max_steps = max_steps; e.terminate_on_success = terminate_on_success; e.seed = seed; return e;
+  }
+};
+
+// group work items by model into CTAs of WARPS_PER_BLOCK warps
+static void make_blocks(int n_models, const std::vector<int>& item_model, std::vector<int>& bm, std::vector<int>& bstart, std::vector<int>& bcount, std::vector<int>& perm) {
+  bm.clear(); bstart.clear(); bcount.clear(); perm.clear();
+  for (int mi = 0; mi < n_models; mi++) {
+    int first = (int)perm.size();
+    for (int i = 0; i < (int)item_model.size(); i++) if (item_model[i] == mi) perm.push_back(i);
+    int cnt = (int)perm.size() - first;
+    for (int o = 0; o < cnt; o += WARPS_PER_BLOCK) { bm.push_back(mi); bstart.push_back(first + o); bcount.push_back(cnt - o < WARPS_PER_BLOCK ? cnt - o : WARPS_PER_BLOCK); }
+  }
+}
+template <class T> static int upload(T** dst, const std::vector<T>& v) {
+  if (*dst) cudaFree(*dst);
+  *dst = nullptr;
+  CK(cudaMalloc((void**)dst, sizeof(T) * (v.size() ? v.size() : 1)));
+  if (!v.empty()) CK(cudaMemcpy(*dst, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" {
+
+int mw_sizeof_model(void) { return (int)sizeof(MwModel); }
+int mw_sizeof_taskconst(void) { return (int)sizeof(MwTaskConst); }
+int mw_sizeof_envstate(void) { return (int)sizeof(MwEnvState); }
+int mw_sizeof_snapshot(void) { return (int)sizeof(MwSnapshot); }
+const char* mw_last_error(void) { return g_err.c_str(); }
+const char* mw_build_info(void) {
+  static char buf[256];
+  snprintf(buf, sizeof(buf), "real=%s maxcon=%d maxefc=%d warps_per_block=%d smem_per_block=%zu", sizeof(real) == 4 ? "float" : "double",
+           MW_MAXCON, MW_MAXEFC, WARPS_PER_BLOCK, smem_bytes());
+  return buf;
+}
+
+int mw_create(mw_engine** out, int device, int n_models, const void* models, const void* taskconsts, const float* const* meshverts, const int* nmeshvert) {
+  if (!out || n_models <= 0 || !models || !taskconsts) return fail(MW_ERR_ARG, "mw_create: bad arguments");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(MW_ERR_CUDA, "mw_create: no such CUDA device (this engine has no CPU path)");
+  CK(cudaSetDevice(device));
+  mw_engine* E = new mw_engine();
+  E->device = device; E->n_models = n_models;
+  E->model_stride = (int)((sizeof(MwModel) + 15) / 16 * 16);
+  std::vector<unsigned char> blob((size_t)E->model_stride * n_models, 0);
+  for (int i = 0; i < n_models; i++) memcpy(blob.data() + (size_t)i * E->model_stride, (const unsigned char*)models + (size_t)i * sizeof(MwModel), sizeof(MwModel));
+  CK(cudaMalloc((void**)&E->d_models, blob.size()));
+  CK(cudaMemcpy(E->d_models, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  CK(cudaMalloc((void**)&E->d_tc, sizeof(MwTaskConst) * n_models));
+  CK(cudaMemcpy(E->d_tc, taskconsts, sizeof(MwTaskConst) * n_models, cudaMemcpyHostToDevice));
+  std::vector<float*> ptrs(n_models, nullptr);
+  for (int i = 0; i < n_models; i++) {
+    int nvt = nmeshvert ? nmeshvert[i] : 0;
+    float* p = nullptr;
+    CK(cudaMalloc((void**)&p, sizeof(float) * 3 * (nvt > 0 ? nvt : 1)));
+    if (nvt > 0) CK(cudaMemcpy(p, meshverts[i], sizeof(float) * 3 * nvt, cudaMemcpyHostToDevice));
+    ptrs[i] = p; E->meshbufs.push_back(p);
+  }
+  CK(cudaMalloc((void**)&E->d_meshptrs, sizeof(float*) * n_models));
+  CK(cudaMemcpy(E->d_meshptrs, ptrs.data(), sizeof(float*) * n_models, cudaMemcpyHostToDevice));
+  CK(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+  CK(cudaFuncSetAttribute(k_snapshot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+  CK(cudaFuncSetAttribute(k_substeps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+  *out = E;
+  return MW_OK;
+}
+
+void mw_destroy(mw_engine* E) {
+  if (!E) return;
+  cudaSetDevice(E->device);
+  cudaFree(E->d_models); cudaFree(E->d_tc); cudaFree(E->d_meshptrs);
+  for (float* p : E->meshbufs) cudaFree(p);
+  cudaFree(E->d_state); cudaFree(E->d_snaps); cudaFree(E->d_goal_first); cudaFree(E->d_goal_count); cudaFree(E->d_diag);
+  cudaFree(E->d_block_model); cudaFree(E->d_block_start); cudaFree(E->d_block_count); cudaFree(E->d_perm);
+  delete E;
+}
+
+int mw_set_envs(mw_engine* E, int n_envs, const int* env_model) {
+  if (!E || n_envs <= 0 || !env_model) return fail(MW_ERR_ARG, "mw_set_envs: bad arguments");
+  CK(cudaSetDevice(E->device));
+  std::vector<int> im(env_model, env_model + n_envs), bm, bs, bc, perm;
+  for (int v : im) if (v < 0 || v >= E->n_models) return fail(MW_ERR_ARG, "mw_set_envs: model index out of range");
+  make_blocks(E->n_models, im, bm, bs, bc, perm);
+  E->n_envs = n_envs; E->n_blocks = (int)bm.size();
+  if (upload(&E->d_block_model, bm) || upload(&E->d_block_start, bs) || upload(&E->d_block_count, bc) || upload(&E->d_perm, perm)) return MW_ERR_CUDA;
+  if (E->d_state) cudaFree(E->d_state);
+  CK(cudaMalloc((void**)&E->d_state, sizeof(MwEnvState) * n_envs));
+  CK(cudaMemset(E->d_state, 0, sizeof(MwEnvState) * n_envs));
+  if (E->d_diag) cudaFree(E->d_diag);
+  CK(cudaMalloc((void**)&E->d_diag, sizeof(int) * 2 * n_envs));
+  CK(cudaMemset(E->d_diag, 0, sizeof(int) * 2 * n_envs));
+  return MW_OK;
+}
+
+int mw_build_snapshots(mw_engine* E, int n, const int* model_idx, const float* rand_vec, const unsigned char* partial, int* ids_out) {
+  if (!E || n <= 0 || !model_idx || !rand_vec || !partial) return fail(MW_ERR_ARG, "mw_build_snapshots: bad arguments");
+  CK(cudaSetDevice(E->device));
+  if (E->n_snaps + n > E->snap_cap) {
+    int cap = (E->n_snaps + n) * 2;
+    MwSnapshot* p = nullptr;
+    CK(cudaMalloc((void**)&p, sizeof(MwSnapshot) * cap));
+    if (E->n_snaps) CK(cudaMemcpy(p, E->d_snaps, sizeof(MwSnapshot) * E->n_snaps, cudaMemcpyDeviceToDevice));
+    cudaFree(E->d_snaps); E->d_snaps = p; E->snap_cap = cap;
+  }
+  std::vector<int> im(model_idx, model_idx + n), bm, bs, bc, perm;
+  for (int v : im) if (v < 0 || v >= E->n_models) return fail(MW_ERR_ARG, "mw_build_snapshots: model index out of range");
+  make_blocks(E->n_models, im, bm, bs, bc, perm);
+  int *d_bm = nullptr, *d_bs = nullptr, *d_bc = nullptr, *d_perm = nullptr; float* d_rv = nullptr; unsigned char* d_po = nullptr;
+  if (upload(&d_bm, bm) || upload(&d_bs, bs) || upload(&d_bc, bc) || upload(&d_perm, perm)) return MW_ERR_CUDA;
+  CK(cudaMalloc((void**)&d_rv, sizeof(float) * 6 * n)); CK(cudaMemcpy(d_rv, rand_vec, sizeof(float) * 6 * n, cudaMemcpyHostToDevice));
+  CK(cudaMalloc((void**)&d_po, n)); CK(cudaMemcpy(d_po, partial, n, cudaMemcpyHostToDevice));
+  k_snapshot<<<(int)bm.size(), BLOCK_THREADS, smem_bytes()>>>(E->dev(), d_bm, d_bs, d_bc, d_perm, d_rv, d_po, E->n_snaps);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  cudaFree(d_bm); cudaFree(d_bs); cudaFree(d_bc); cudaFree(d_perm); cudaFree(d_rv); cudaFree(d_po);
+  if (ids_out) for (int i = 0; i < n; i++) ids_out[i] = E->n_snaps + i;
+  E->n_snaps += n; E->launches++;
+  return MW_OK;
+}
+int mw_num_snapshots(const mw_engine* E) { return E ? E->n_snaps : 0; }
+int mw_get_snapshots(mw_engine* E, int first, int n, void* out) {
+  if (!E || first < 0 || first + n > E->n_snaps) return fail(MW_ERR_ARG, "mw_get_snapshots: range");
+  CK(cudaSetDevice(E->device));
+  CK(cudaMemcpy(out, E->d_snaps + first, sizeof(MwSnapshot) * n, cudaMemcpyDeviceToHost));
+  return MW_OK;
+}
+
+int mw_reset(mw_engine* E, int n, const int* env_ids, const int* snapshot_ids, float* obs, int obs_stride, void* stream) {
+  if (!E || !E->d_state || n <= 0 || !snapshot_ids || !obs || obs_stride < 39) return fail(MW_ERR_ARG, "mw_reset: bad arguments");
+  CK(cudaSetDevice(E->device));
+  k_reset<<<(n * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(E->dev(), n, env_ids, snapshot_ids, obs, obs_stride);
+  CK(cudaGetLastError());
+  E->launches++;
+  return MW_OK;
+}
+
+int mw_step(mw_engine* E, const float* actions, float* obs, int obs_stride, float* reward, unsigned char* terminated, unsigned char* truncated,
+            float* info, float* final_obs, float* final_info, const int* next_snapshot, void* stream) {
+  if (!E || !E->d_state) return fail(MW_ERR_STATE, "mw_step: mw_set_envs not called");
+  if (!actions || !obs || !reward || !terminated || !truncated || !info || obs_stride < 39) return fail(MW_ERR_ARG, "mw_step: bad arguments");
+  if (!next_snapshot && !E->d_goal_first) return fail(MW_ERR_STATE, "mw_step: no next_snapshot and no goal sets for the device sampler");
+  CK(cudaSetDevice(E->device));
+  k_step<<<E->n_blocks, BLOCK_THREADS, smem_bytes(), (cudaStream_t)stream>>>(E->dev(), E->d_block_model, E->d_block_start, E->d_block_count, E->d_perm,
+      actions, obs, obs_stride, reward, terminated, truncated, info, final_obs, final_info, next_snapshot);
+  CK(cudaGetLastError());
+  E->launches++; E->env_steps += (unsigned long long)E->n_envs;
+  return MW_OK;
+}
+
+int mw_set_options(mw_engine* E, int max_episode_steps, int terminate_on_success, unsigned long long seed) {
+  if (!E || max_episode_steps <= 0) return fail(MW_ERR_ARG, "mw_set_options: bad arguments");
+  E->max_steps = max_episode_steps; E->terminate_on_success = terminate_on_success; E->seed = seed;
+  return MW_OK;
+}
+int mw_set_goal_sets(mw_engine* E, const int* first, const int* count) {
+  if (!E || !E->n_envs || !first || !count) return fail(MW_ERR_ARG, "mw_set_goal_sets: bad arguments");
+  CK(cudaSetDevice(E->device));
+  std::vector<int> f(first, first + E->n_envs), c(count, count + E->n_envs);
+  for (int i = 0; i < E->n_envs; i++) if (c[i] <= 0 || f[i] < 0 || f[i] + c[i] > E->n_snaps) return fail(MW_ERR_ARG, "mw_set_goal_sets: range outside the snapshot table");
+  if (upload(&E->d_goal_first, f) || upload(&E->d_goal_count, c)) return MW_ERR_CUDA;
+  return MW_OK;
+}
+int mw_get_state(mw_engine* E, void* out) {
+  if (!E || !E->d_state || !out) return fail(MW_ERR_ARG, "mw_get_state");
+  CK(cudaSetDevice(E->device));
+  CK(cudaMemcpy(out, E->d_state, sizeof(MwEnvState) * E->n_envs, cudaMemcpyDeviceToHost));
+  return MW_OK;
+}
+int mw_set_state(mw_engine* E, const void* in) {
+  if (!E || !E->d_state || !in) return fail(MW_ERR_ARG, "mw_set_state");
+  CK(cudaSetDevice(E->device));
+  CK(cudaMemcpy(E->d_state, in, sizeof(MwEnvState) * E->n_envs, cudaMemcpyHostToDevice));
+  return MW_OK;
+}
+int mw_debug_substeps(mw_engine* E, int nstep, const float* ctrl2, void* stream) {
+  if (!E || !E->d_state || nstep < 0 || !ctrl2) return fail(MW_ERR_ARG, "mw_debug_substeps");
+  CK(cudaSetDevice(E->device));
+  k_substeps<<<E->n_blocks, BLOCK_THREADS, smem_bytes(), (cudaStream_t)stream>>>(E->dev(), E->d_block_model, E->d_block_start, E->d_block_count, E->d_perm, nstep, ctrl2[0], ctrl2[1]);
+  CK(cudaGetLastError());
+  E->launches++;
+  return MW_OK;
+}
+int mw_get_counters(mw_engine* E, unsigned long long* out5) {
+  if (!E || !out5) return fail(MW_ERR_ARG, "mw_get_counters");
+  CK(cudaSetDevice(E->device));
+  std::vector<int> diag(2 * (size_t)(E->n_envs > 0 ? E->n_envs : 0));
+  if (E->n_envs) { CK(cudaMemcpy(diag.data(), E->d_diag, sizeof(int) * diag.size(), cudaMemcpyDeviceToHost)); CK(cudaMemset(E->d_diag, 0, sizeof(int) * diag.size())); }
+  unsigned long long dropped = 0, iters = 0;
+  for (int i = 0; i < E->n_envs; i++) { dropped += diag[2 * i]; iters += diag[2 * i + 1]; }
+  out5[0] = E->launches; out5[1] = E->env_steps; out5[2] = dropped; out5[3] = iters; out5[4] = E->env_steps * 6ull;
+  E->launches = 0; E->env_steps = 0;
+  return MW_OK;
+}
+
+}  // extern "C"

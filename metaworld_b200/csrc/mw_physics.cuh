@@ -1,0 +1,836 @@
+// One-environment-per-warp forward dynamics + semi-implicit Euler step.
+//
+// Hot path replaced: the reference's `do_simulation` -> `mujoco.mj_step(nstep=5)` and `mj_forward`
+// (metaworld/sawyer_xyz_env.py:595,620) -- MuJoCo's CPU pipeline [3P] -- for the Meta-World MJCF
+// feature set.  A warp owns one environment for the whole env step (5 substeps + 1 forward), so the
+// state makes a single HBM round trip; all intermediates live in the warp's shared-memory scratch.
+//
+// Lane mapping: lane d <-> degree of freedom d (nv <= 17) for Jacobian columns, inertia columns and
+// dense vectors; lane r <-> constraint row / contact for per-row work; lane p <-> candidate pair in the
+// broadphase / analytic narrowphase.  Reductions are warp shuffles in a fixed order (deterministic).
+#pragma once
+#include "mw_model.h"
+#include "mw_collide.cuh"
+
+#define NVP 17               // row stride of the dense nv x nv / nefc x nv matrices (odd: conflict-free columns)
+#ifndef MW_MAXCON
+#define MW_MAXCON 24
+#endif
+#define MW_MAXSCALAR 24      // weld (6) + joint-limit rows
+#define MW_MAXEFC (MW_MAXSCALAR + 4 * MW_MAXCON)
+
+enum { JT_FREE = 0, JT_BALL, JT_SLIDE, JT_HINGE };
+
+struct Contact {
+  real pos[3], frame[9], dist, mu, fr1, fr3, incl;
+  real solref[2], solimp[5];
+  real H[10];              // packed symmetric dim x dim cone Hessian (row-major upper)
+  real fn;                 // normal force of the last solve
+  int dim, g1, g2, row, hzone;
+};
+
+// region U is time-shared: (a) geom world poses + EPA workspace during collision, (b) efc_J afterwards
+#define MW_UWORDS_J (MW_MAXEFC * NVP)
+#define MW_UWORDS_C (MW_MAXGEOM * 12 + EPA_WS_WORDS)
+#define MW_UWORDS (MW_UWORDS_J > MW_UWORDS_C ? MW_UWORDS_J : MW_UWORDS_C)
+
+struct WarpScratch {
+  real lpos[MW_MAXLINK][3], lquat[MW_MAXLINK][4], lmat[MW_MAXLINK][9];
+  real daxis[MW_MAXDOF][3], danchor[MW_MAXDOF][3];
+  real qpos[MW_MAXNQ], qvel[MW_MAXDOF], warm[MW_MAXDOF];
+  real ctrl[2], mocap_pos[3], mocap_quat[4], shift[3];
+  real qfrc_smooth[MW_MAXDOF], qacc_smooth[MW_MAXDOF], qfrc_con[MW_MAXDOF], qacc[MW_MAXDOF];
+  real vMa[MW_MAXDOF], vSearch[MW_MAXDOF], vMs[MW_MAXDOF], vTmp[MW_MAXDOF];
+  real M[MW_MAXDOF * NVP], H[MW_MAXDOF * NVP];
+  real U[MW_UWORDS];
+  real eD[MW_MAXEFC], eAref[MW_MAXEFC], eJar[MW_MAXEFC], eJv[MW_MAXEFC], eF[MW_MAXEFC], eHd[MW_MAXEFC];
+  Contact con[MW_MAXCON];
+  unsigned short cand[64];
+  int ncon, nefc, nscalar, nweld, solver_iter, ncon_dropped;
+};
+
+#define SYNCW() __syncwarp()
+
+// ------------------------------------------------------------------ kinematics  [MuJoCo mj_kinematics]
+// Sequential over the (short) link chain; every lane computes the same values, lane 0 stores.
+__device__ __noinline__ void mw_kinematics(const MwModel* __restrict__ m, WarpScratch* w, int lane) {
+  const int nl = m->nlink;
+  for (int l = 0; l < nl; l++) {
+    int p = m->link_parent[l];
+    real pos[3], quat[4], R[9];
+    if (p < 0) {
+      if (m->link_shift[l]) { for (int i = 0; i < 3; i++) pos[i] = m->link_pos[l][i] + w->shift[i]; }
+      else { for (int i = 0; i < 3; i++) pos[i] = m->link_pos[l][i]; }
+      for (int i = 0; i < 4; i++) quat[i] = m->link_quat[l][i];
+    } else {
+      real lp[3] = {m->link_pos[l][0], m->link_pos[l][1], m->link_pos[l][2]};
+      real lq[4] = {m->link_quat[l][0], m->link_quat[l][1], m->link_quat[l][2], m->link_quat[l][3]};
+      real t[3]; mat_mulvec(t, w->lmat[p], lp); v3add(pos, w->lpos[p], t);
+      quat_mul(quat, w->lquat[p], lq);
+    }
+    const int jt = m->link_jtype[l], qa = m->link_qadr[l], da = m->link_dadr[l];
+    if (jt == JT_FREE) {
+      real q[4] = {w->qpos[qa + 3], w->qpos[qa + 4], w->qpos[qa + 5], w->qpos[qa + 6]};
+      quat_normalize(q);
+      for (int i = 0; i < 3; i++) pos[i] = w->qpos[qa + i];
+      for (int i = 0; i < 4; i++) quat[i] = q[i];
+      quat2mat(R, quat);
+      if (lane == 0) {
+        for (int i = 0; i < 4; i++) w->qpos[qa + 3 + i] = q[i];
+        for (int i = 0; i < 3; i++) {
+          for (int k = 0; k < 3; k++) { w->daxis[da + i][k] = (i == k); w->danchor[da + i][k] = pos[k]; }
+          w->daxis[da + 3 + i][0] = R[i]; w->daxis[da + 3 + i][1] = R[3 + i]; w->daxis[da + 3 + i][2] = R[6 + i];
+          for (int k = 0; k < 3; k++) w->danchor[da + 3 + i][k] = pos[k];
+        }
+      }
+    } else {
+      real jax[3] = {m->link_jaxis[l][0], m->link_jaxis[l][1], m->link_jaxis[l][2]};
+      real jp[3] = {m->link_jpos[l][0], m->link_jpos[l][1], m->link_jpos[l][2]};
+      real axis[3], anchor[3], t[3];
+      quat_normalize(quat);
+      quat2mat(R, quat);
+      mat_mulvec(axis, R, jax);
+      mat_mulvec(t, R, jp); v3add(anchor, pos, t);
+      real q = w->qpos[qa] - (real)m->qpos0[qa];
+      if (jt == JT_SLIDE) v3addscl(pos, pos, axis, q);
+      else {
+        real qr[4], qn[4];
+        quat_axisangle(qr, jax, q);
+        quat_mul(qn, quat, qr);
+        for (int i = 0; i < 4; i++) quat[i] = qn[i];
+        quat_normalize(quat);
+        quat2mat(R, quat);
+        mat_mulvec(t, R, jp); v3sub(pos, anchor, t);
+      }
+      if (lane == 0) for (int k = 0; k < 3; k++) { w->daxis[da][k] = axis[k]; w->danchor[da][k] = anchor[k]; }
+    }
+    quat_normalize(quat);
+    quat2mat(R, quat);
+    if (lane == 0) {
+      for (int i = 0; i < 3; i++) w->lpos[l][i] = pos[i];
+      for (int i = 0; i < 4; i++) w->lquat[l][i] = quat[i];
+      for (int i = 0; i < 9; i++) w->lmat[l][i] = R[i];
+    }
+    SYNCW();
+  }
+}
+
+// world pose of a frame / geom attached to link l (or to the world, optionally riding on the shift)
+DEV void mw_attach(const WarpScratch* w, int link, int shift, const float* lp, real* pos) {
+  real p[3] = {lp[0], lp[1], lp[2]};
+  if (link < 0) { for (int i = 0; i < 3; i++) pos[i] = p[i] + (shift ? w->shift[i] : (real)0); }
+  else { real t[3]; mat_mulvec(t, w->lmat[link], p); v3add(pos, w->lpos[link], t); }
+}
+DEV void mw_frame_pos(const MwModel* m, const WarpScratch* w, int f, real* pos) {
+  mw_attach(w, m->frame_link[f], m->frame_shift[f], m->frame_pos[f], pos);
+}
+DEV void mw_frame_quat(const MwModel* m, const WarpScratch* w, int f, real* q) {
+  real fq[4] = {m->frame_quat[f][0], m->frame_quat[f][1], m->frame_quat[f][2], m->frame_quat[f][3]};
+  int l = m->frame_link[f];
+  if (l < 0) { for (int i = 0; i < 4; i++) q[i] = fq[i]; }
+  else quat_mul(q, w->lquat[l], fq);
+  quat_normalize(q);
+}
+
+// per-lane dof description held in registers
+struct LaneDof { real ax[3], an[3]; int rot; int valid; };
+DEV void mw_lane_dof(const MwModel* m, const WarpScratch* w, int lane, LaneDof* L) {
+  L->valid = lane < m->nv;
+  int d = L->valid ? lane : 0;
+  for (int k = 0; k < 3; k++) { L->ax[k] = L->valid ? w->daxis[d][k] : (real)0; L->an[k] = w->danchor[d][k]; }
+  int l = m->dof_link[d];
+  int jt = m->link_jtype[l];
+  L->rot = (jt == JT_HINGE) || (jt == JT_FREE && (d - m->link_dadr[l]) >= 3);
+}
+// column `lane` of the Jacobian of a world point on a body whose ancestor-dof mask is `mask`
+DEV void mw_jac_col(const LaneDof& L, unsigned mask, int lane, const real* point, real* jp, real* jr) {
+  if (L.valid && ((mask >> lane) & 1u)) {
+    if (L.rot) { real r[3]; v3sub(r, point, L.an); v3cross(jp, L.ax, r); v3copy(jr, L.ax); }
+    else { v3copy(jp, L.ax); v3zero(jr); }
+  } else { v3zero(jp); v3zero(jr); }
+}
+
+// ------------------------------------------------------------------ inertia  [MuJoCo mj_crb]
+// M = sum_links S^T I_link S with spatial vectors about the world origin; lane d owns column d.
+__device__ __noinline__ void mw_mass_matrix(const MwModel* __restrict__ m, WarpScratch* w, const LaneDof& L, int lane) {
+  const int nv = m->nv;
+  for (int i = lane; i < nv * NVP; i += 32) w->M[i] = 0;
+  SYNCW();
+  real Sa[3], Sl[3];   // spatial motion vector of this lane's dof
+  if (L.rot) { v3copy(Sa, L.ax); v3cross(Sl, L.an, L.ax); } else { v3zero(Sa); v3copy(Sl, L.ax); }
+  if (!L.valid) { v3zero(Sa); v3zero(Sl); }
+  for (int l = 0; l < m->nlink; l++) {
+    real mass = m->link_mass[l];
+    if (mass <= 0) continue;
+    unsigned mask = m->link_dofmask[l];
+    const real* R = w->lmat[l];
+    real cl[3] = {m->link_com[l][0], m->link_com[l][1], m->link_com[l][2]}, c[3], t[3];
+    mat_mulvec(t, R, cl); v3add(c, w->lpos[l], t);
+    // world inertia about the COM: R I R^T
+    real I6[6] = {m->link_inertia[l][0], m->link_inertia[l][1], m->link_inertia[l][2], m->link_inertia[l][3], m->link_inertia[l][4], m->link_inertia[l][5]};
+    real Il[9] = {I6[0], I6[3], I6[4], I6[3], I6[1], I6[5], I6[4], I6[5], I6[2]}, T[9], Iw[9];
+    mat_mul(T, R, Il);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Iw[3 * i + j] = T[3 * i] * R[3 * j] + T[3 * i + 1] * R[3 * j + 1] + T[3 * i + 2] * R[3 * j + 2];
+    // momentum of this lane's dof: p = m (v + w x c), Lang = Iw w + c x p
+    real pl[3], La[3];
+    v3cross(t, Sa, c); for (int i = 0; i < 3; i++) pl[i] = mass * (Sl[i] + t[i]);
+    mat_mulvec(La, Iw, Sa); v3cross(t, c, pl); v3add(La, La, t);
+    bool mine = L.valid && ((mask >> lane) & 1u);
+    unsigned rem = mask;
+    while (rem) {
+      int e = __ffs(rem) - 1; rem &= rem - 1;
+      real ea[3] = {bcast(Sa[0], e), bcast(Sa[1], e), bcast(Sa[2], e)};
+      real el[3] = {bcast(Sl[0], e), bcast(Sl[1], e), bcast(Sl[2], e)};
+      if (mine) w->M[e * NVP + lane] += v3dot(ea, La) + v3dot(el, pl);
+    }
+  }
+  if (L.valid) w->M[lane * NVP + lane] += m->dof_armature[lane];
+  SYNCW();
+}
+
+// in-place dense Cholesky of the lower triangle of A (stride NVP); lane i owns row i.  returns min pivot
+DEV real mw_chol(real* A, int nv, int lane) {
+  real minpiv = (real)1e30;
+  for (int j = 0; j < nv; j++) {
+    real s = 0;
+    if (lane >= j && lane < nv) {
+      s = A[lane * NVP + j];
+      for (int k = 0; k < j; k++) s -= A[lane * NVP + k] * A[j * NVP + k];
+    }
+    real piv = bcast(s, j);
+    minpiv = fmin(minpiv, piv);
+    piv = sqrt(fmax(piv, (real)1e-30));
+    if (lane == j) A[j * NVP + j] = piv;
+    else if (lane > j && lane < nv) A[lane * NVP + j] = s / piv;
+    SYNCW();
+  }
+  return minpiv;
+}
+// solve L L^T x = b ; lane i holds b_i / returns x_i
+DEV real mw_chol_solve(const real* Lm, real b, int nv, int lane) {
+  real y = b;
+  for (int j = 0; j < nv; j++) {
+    real xj = bcast(y, j) / Lm[j * NVP + j];
+    if (lane == j) y = xj;
+    else if (lane > j && lane < nv) y -= Lm[lane * NVP + j] * xj;
+  }
+  for (int j = nv - 1; j >= 0; j--) {
+    real xj = bcast(y, j) / Lm[j * NVP + j];
+    if (lane == j) y = xj;
+    else if (lane < j) y -= Lm[j * NVP + lane] * xj;
+  }
+  return lane < nv ? y : (real)0;
+}
+
+// ------------------------------------------------------------------ bias forces  [MuJoCo mj_comVel + mj_rne]
+DEV void cross_motion(real* r, const real* v, const real* s) {
+  real a[3], b[3], c[3];
+  v3cross(a, v, s); v3cross(b, v, s + 3); v3cross(c, v + 3, s);
+  r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; r[3] = b[0] + c[0]; r[4] = b[1] + c[1]; r[5] = b[2] + c[2];
+}
+// returns qfrc_bias for this lane's dof.  Uses w->H as scratch (cvel/cacc/cfrc per link).
+__device__ __noinline__ real mw_rne_bias(const MwModel* __restrict__ m, WarpScratch* w, const LaneDof& L, int lane) {
+  real* cvel = w->H; real* cacc = w->H + 6 * MW_MAXLINK; real* cfrc = w->H + 12 * MW_MAXLINK;
+  const int nl = m->nlink;
+  for (int l = 0; l < nl; l++) {
+    int p = m->link_parent[l];
+    real v[6], a[6];
+    if (p < 0) { for (int c = 0; c < 6; c++) { v[c] = 0; a[c] = 0; } a[3] = -m->gravity[0]; a[4] = -m->gravity[1]; a[5] = -m->gravity[2]; }
+    else { for (int c = 0; c < 6; c++) { v[c] = cvel[6 * p + c]; a[c] = cacc[6 * p + c]; } }
+    int jt = m->link_jtype[l], da = m->link_dadr[l];
+    if (jt == JT_FREE) {
+      real vb[6];
+      for (int i = 0; i < 3; i++) {   // world-fixed translation axes
+        real S[6] = {0, 0, 0, w->daxis[da + i][0], w->daxis[da + i][1], w->daxis[da + i][2]}, Sd[6];
+        cross_motion(Sd, v, S);
+        real qd = w->qvel[da + i];
+        for (int c = 0; c < 6; c++) { a[c] += Sd[c] * qd; }
+        for (int c = 0; c < 6; c++) v[c] += S[c] * qd;
+      }
+      for (int c = 0; c < 6; c++) vb[c] = v[c];
+      for (int i = 3; i < 6; i++) {   // body-fixed rotation axes: all three see the same velocity
+        real S[6], Sd[6];
+        for (int k = 0; k < 3; k++) S[k] = w->daxis[da + i][k];
+        v3cross(S + 3, w->danchor[da + i], w->daxis[da + i]);
+        cross_motion(Sd, vb, S);
+        real qd = w->qvel[da + i];
+        for (int c = 0; c < 6; c++) { a[c] += Sd[c] * qd; v[c] += S[c] * qd; }
+      }
+    } else {
+      real S[6], Sd[6];
+      if (jt == JT_HINGE) { for (int k = 0; k < 3; k++) S[k] = w->daxis[da][k]; v3cross(S + 3, w->danchor[da], w->daxis[da]); }
+      else { S[0] = S[1] = S[2] = 0; for (int k = 0; k < 3; k++) S[3 + k] = w->daxis[da][k]; }
+      cross_motion(Sd, v, S);
+      real qd = w->qvel[da];
+      for (int c = 0; c < 6; c++) { v[c] += S[c] * qd; a[c] += Sd[c] * qd; }
+    }
+    // body force f = I a + v x* (I v)
+    real mass = m->link_mass[l];
+    real f[6] = {0, 0, 0, 0, 0, 0};
+    if (mass > 0) {
+      const real* R = w->lmat[l];
+      real cl[3] = {m->link_com[l][0], m->link_com[l][1], m->link_com[l][2]}, c[3], t[3], u[3];
+      mat_mulvec(t, R, cl); v3add(c, w->lpos[l], t);
+      real I6[6] = {m->link_inertia[l][0], m->link_inertia[l][1], m->link_inertia[l][2], m->link_inertia[l][3], m->link_inertia[l][4], m->link_inertia[l][5]};
+      real Il[9] = {I6[0], I6[3], I6[4], I6[3], I6[1], I6[5], I6[4], I6[5], I6[2]}, T[9], Iw[9];
+      mat_mul(T, R, Il);
+      for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Iw[3 * i + j] = T[3 * i] * R[3 * j] + T[3 * i + 1] * R[3 * j + 1] + T[3 * i + 2] * R[3 * j + 2];
+      real pl[3], Lm[3], pa[3], La[3];
+      v3cross(t, v, c); for (int i = 0; i < 3; i++) pl[i] = mass * (v[3 + i] + t[i]);
+      mat_mulvec(Lm, Iw, v); v3cross(t, c, pl); v3add(Lm, Lm, t);
+      v3cross(t, a, c); for (int i = 0; i < 3; i++) pa[i] = mass * (a[3 + i] + t[i]);
+      mat_mulvec(La, Iw, a); v3cross(t, c, pa); v3add(La, La, t);
+      v3cross(t, v, Lm); v3cross(u, v + 3, pl);
+      for (int i = 0; i < 3; i++) f[i] = La[i] + t[i] + u[i];
+      v3cross(t, v, pl);
+      for (int i = 0; i < 3; i++) f[3 + i] = pa[i] + t[i];
+    }
+    if (lane == 0) for (int c = 0; c < 6; c++) { cvel[6 * l + c] = v[c]; cacc[6 * l + c] = a[c]; cfrc[6 * l + c] = f[c]; }
+    SYNCW();
+  }
+  if (lane == 0) for (int l = nl - 1; l >= 0; l--) { int p = m->link_parent[l]; if (p >= 0) for (int c = 0; c < 6; c++) cfrc[6 * p + c] += cfrc[6 * l + c]; }
+  SYNCW();
+  real bias = 0;
+  if (L.valid) {
+    const real* f = cfrc + 6 * m->dof_link[lane];
+    real Sa[3], Sl[3];
+    if (L.rot) { v3copy(Sa, L.ax); v3cross(Sl, L.an, L.ax); } else { v3zero(Sa); v3copy(Sl, L.ax); }
+    bias = v3dot(Sa, f) + v3dot(Sl, f + 3);
+  }
+  SYNCW();
+  return bias;
+}
+
+// ------------------------------------------------------------------ collision  [MuJoCo mj_collision]
+DEV void mw_load_shape(const MwModel* m, const real* gpose, const float* meshvert, int g, DShape* s) {
+  s->type = m->geom_type[g];
+  for (int i = 0; i < 3; i++) { s->pos[i] = gpose[12 * g + i]; s->size[i] = m->geom_size[g][i]; }
+  for (int i = 0; i < 9; i++) s->mat[i] = gpose[12 * g + 3 + i];
+  s->vert = meshvert + 3 * m->geom_meshadr[g]; s->nvert = m->geom_meshnum[g];
+}
+DEV void make_frame(real* fr) {
+  v3normalize(fr);
+  real* y = fr + 3; real* z = fr + 6;
+  v3zero(y);
+  if (fr[1] < (real)0.5 && fr[1] > (real)-0.5) y[1] = 1; else y[2] = 1;
+  real dp = v3dot(fr, y);
+  v3addscl(y, y, fr, -dp);
+  v3normalize(y);
+  v3cross(z, fr, y);
+}
+DEV void mw_store_contact(const MwModel* m, WarpScratch* w, int slot, const RawCon& rc, int pair) {
+  Contact* c = &w->con[slot];
+  int prm = m->pair_param[pair];
+  const float* P = m->param[prm];
+  c->dist = rc.dist;
+  for (int k = 0; k < 3; k++) { c->pos[k] = rc.pos[k]; c->frame[k] = rc.normal[k]; }
+  make_frame(c->frame);
+  c->g1 = m->pair_g1[pair]; c->g2 = m->pair_g2[pair];
+  c->incl = P[1]; c->dim = (int)P[2]; c->fr1 = P[3]; c->fr3 = P[4]; c->mu = P[3];
+  c->solref[0] = P[5]; c->solref[1] = P[6];
+  for (int k = 0; k < 5; k++) c->solimp[k] = P[7 + k];
+  c->row = -1; c->fn = 0; c->hzone = 0;
+}
+
+__device__ __noinline__ void mw_collide(const MwModel* __restrict__ m, const float* __restrict__ meshvert, WarpScratch* w, int lane) {
+  real* gpose = w->U;                                   // [ngeom][12]
+  EpaWs* epa = (EpaWs*)(w->U + MW_MAXGEOM * 12);
+  const int ng = m->ngeom, np = m->npair;
+  for (int g = lane; g < ng; g += 32) {
+    int l = m->geom_link[g];
+    real pos[3]; mw_attach(w, l, m->geom_shift[g], m->geom_pos[g], pos);
+    real Rl[9]; for (int i = 0; i < 9; i++) Rl[i] = m->geom_mat[g][i];
+    real Rw[9];
+    if (l < 0) { for (int i = 0; i < 9; i++) Rw[i] = Rl[i]; } else mat_mul(Rw, w->lmat[l], Rl);
+    for (int i = 0; i < 3; i++) gpose[12 * g + i] = pos[i];
+    for (int i = 0; i < 9; i++) gpose[12 * g + 3 + i] = Rw[i];
+  }
+  if (lane == 0) { w->ncon = 0; w->ncon_dropped = 0; }
+  SYNCW();
+  int ncon = 0;
+  for (int base = 0; base < np; base += 32) {
+    int p = base + lane;
+    // ---- broadphase cull (conservative: never removes a pair that is within margin)
+    bool keep = false; int g1 = 0, g2 = 0; real margin = 0;
+    if (p < np) {
+      g1 = m->pair_g1[p]; g2 = m->pair_g2[p];
+      margin = m->param[m->pair_param[p]][0];
+      int t1 = m->geom_type[g1], t2 = m->geom_type[g2];
+      const real* p1 = gpose + 12 * g1; const real* p2 = gpose + 12 * g2;
+      real r1 = m->geom_rbound[g1], r2 = m->geom_rbound[g2];
+      if (t1 == G_PLANE) {
+        real n[3], t[3]; mat_col(n, p1 + 3, 2); v3sub(t, p2, p1);
+        keep = v3dot(t, n) <= r2 + margin;
+      } else {
+        real t[3]; v3sub(t, p2, p1);
+        real bound = r1 + r2 + margin;
+        keep = v3dot(t, t) <= bound * bound;
+        if (keep && t2 == G_BOX) {   // bounding sphere of g1 against the exact box g2
+          real cl[3], dd = 0; mat_tmulvec(cl, p2 + 3, t); // centre of g1 in box-2 frame is -R2^T t
+          for (int i = 0; i < 3; i++) { real e = fabs(cl[i]) - m->geom_size[g2][i]; if (e > 0) dd += e * e; }
+          real b = r1 + margin; keep = dd <= b * b;
+        }
+        if (keep && t1 == G_BOX) {
+          real cl[3], dd = 0; mat_tmulvec(cl, p1 + 3, t);
+          for (int i = 0; i < 3; i++) { real e = fabs(cl[i]) - m->geom_size[g1][i]; if (e > 0) dd += e * e; }
+          real b = r2 + margin; keep = dd <= b * b;
+        }
+      }
+    }
+    // ---- analytic pairs: one pair per lane
+    bool analytic = keep && pair_is_analytic(m->geom_type[g1], m->geom_type[g2]);
+    RawCon rc[8]; int cnt = 0;
+    if (analytic) {
+      DShape a, b; mw_load_shape(m, gpose, meshvert, g1, &a); mw_load_shape(m, gpose, meshvert, g2, &b);
+      cnt = narrow_analytic(a, b, margin, rc);
+    }
+    // deterministic compaction: exclusive prefix of counts over lanes
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULLMASK, incl, o); if (lane >= o) incl += t; }
+    int start = ncon + incl - cnt;
+    for (int k = 0; k < cnt; k++) if (start + k < MW_MAXCON) mw_store_contact(m, w, start + k, rc[k], p);
+    ncon += __shfl_sync(FULLMASK, incl, 31);
+    // ---- general convex pairs: the whole warp works on one pair at a time
+    unsigned cm = __ballot_sync(FULLMASK, keep && !analytic);
+    while (cm) {
+      int src = __ffs(cm) - 1; cm &= cm - 1;
+      int pp = base + src;
+      int h1 = m->pair_g1[pp], h2 = m->pair_g2[pp];
+      DShape a, b; mw_load_shape(m, gpose, meshvert, h1, &a); mw_load_shape(m, gpose, meshvert, h2, &b);
+      real mg = m->param[m->pair_param[pp]][0];
+      RawCon r1; int c1;
+      if (a.type == G_PLANE) {   // plane - mesh: support vertex against the plane
+        real n[3], nd[3], sp[3], t[3]; mat_col(n, a.mat, 2); v3scl(nd, n, -1);
+        support_shape(b, nd, sp, lane);
+        v3sub(t, sp, a.pos);
+        r1.dist = v3dot(t, n); v3copy(r1.normal, n); v3addscl(r1.pos, sp, n, -(real)0.5 * r1.dist);
+        c1 = r1.dist <= mg;
+      } else c1 = convex_pair(a, b, mg, &r1, epa, lane);
+      if (c1) { if (ncon < MW_MAXCON && lane == 0) mw_store_contact(m, w, ncon, r1, pp); ncon++; }
+    }
+  }
+  SYNCW();
+  if (lane == 0) { w->ncon = ncon < MW_MAXCON ? ncon : MW_MAXCON; w->ncon_dropped = ncon > MW_MAXCON ? ncon - MW_MAXCON : 0; }
+  SYNCW();
+}
+
+// ------------------------------------------------------------------ constraint rows  [MuJoCo mj_makeConstraint]
+struct RowParam { real K, B, imp; };
+DEV RowParam mw_impedance(real pos_minus_margin, const real* solref, const real* solimp, real timestep) {
+  real lo = fmin(fmax(solimp[0], (real)0.0001), (real)0.9999), hi = fmin(fmax(solimp[1], (real)0.0001), (real)0.9999);
+  real width = fmax(solimp[2], (real)0), mid = fmin(fmax(solimp[3], (real)0.0001), (real)0.9999), power = fmax(solimp[4], (real)1);
+  real imp;
+  if (lo == hi || width <= MW_EPS) imp = (real)0.5 * (lo + hi);
+  else {
+    real x = fabs(pos_minus_margin) / width;
+    if (x >= 1) imp = hi;
+    else if (x <= 0) imp = lo;
+    else {
+      real y;
+      if (power == 1) y = x;
+      else if (x <= mid) y = pow(x, power) / pow(mid, power - 1);
+      else y = 1 - pow(1 - x, power) / pow(1 - mid, power - 1);
+      imp = lo + y * (hi - lo);
+    }
+  }
+  RowParam r; r.imp = imp;
+  if (solref[0] > 0) {
+    real tc = fmax(solref[0], 2 * timestep), dr = solref[1];
+    r.K = 1 / fmax(MW_EPS, hi * hi * tc * tc * dr * dr);
+    r.B = 2 / fmax(MW_EPS, hi * tc);
+  } else { r.K = -solref[0] / fmax(MW_EPS, hi * hi); r.B = -solref[1] / fmax(MW_EPS, hi); }
+  return r;
+}
+
+__device__ __noinline__ void mw_make_constraints(const MwModel* __restrict__ m, WarpScratch* w, const LaneDof& L, int lane) {
+  real* J = w->U;
+  const int nv = m->nv;
+  const real h = m->timestep;
+  // ---- weld rows 0..5 (mocap -> hand)
+  int wl = m->weld_link;
+  real ph[3], qh[4];
+  { real wp[3] = {m->weld_pos[0], m->weld_pos[1], m->weld_pos[2]}, t[3]; mat_mulvec(t, w->lmat[wl], wp); v3add(ph, w->lpos[wl], t);
+    real wq[4] = {m->weld_quat[0], m->weld_quat[1], m->weld_quat[2], m->weld_quat[3]}; quat_mul(qh, w->lquat[wl], wq); }
+  real qm[4] = {w->mocap_quat[0], w->mocap_quat[1], w->mocap_quat[2], w->mocap_quat[3]};
+  quat_normalize(qm);
+  real q[4] = {-qm[0], -qm[1], -qm[2], -qm[3]};            // q_mocap * relpose(-1,0,0,0)
+  real q1n[4] = {qh[0], -qh[1], -qh[2], -qh[3]}, q2[4];
+  quat_mul(q2, q1n, q);
+  const real ts = m->weld_torquescale;
+  real cpos[6] = {w->mocap_pos[0] - ph[0], w->mocap_pos[1] - ph[1], w->mocap_pos[2] - ph[2], ts * q2[1], ts * q2[2], ts * q2[3]};
+  {
+    real jp[3], jr[3];
+    mw_jac_col(L, m->link_dofmask[wl], lane, ph, jp, jr);
+    real axq[4] = {0, -jr[0], -jr[1], -jr[2]}, a4[4], b4[4];
+    quat_mul(a4, q1n, axq); quat_mul(b4, a4, q);
+    if (lane < nv) for (int k = 0; k < 3; k++) { J[k * NVP + lane] = -jp[k]; J[(3 + k) * NVP + lane] = (real)0.5 * ts * b4[1 + k]; }
+  }
+  int nrow = 6;
+  // ---- joint limits
+  bool lim_lo = false, lim_hi = false; real ldist = 0;
+  if (L.valid && m->dof_limited[lane]) {
+    real qv = w->qpos[m->dof_qadr[lane]];
+    real dlo = qv - m->dof_lo[lane], dhi = m->dof_hi[lane] - qv;
+    if (dlo < 0) { lim_lo = true; ldist = dlo; } else if (dhi < 0) { lim_hi = true; ldist = dhi; }
+  }
+  unsigned lm = __ballot_sync(FULLMASK, lim_lo || lim_hi);
+  int nlim = __popc(lm);
+  if (nrow + nlim > MW_MAXSCALAR) { nlim = MW_MAXSCALAR - nrow; }
+  int myrank = __popc(lm & ((1u << lane) - 1));
+  for (int r = 0; r < nlim; r++) if (lane < nv) J[(nrow + r) * NVP + lane] = 0;
+  SYNCW();
+  if ((lim_lo || lim_hi) && myrank < nlim) J[(nrow + myrank) * NVP + lane] = lim_lo ? (real)1 : (real)-1;
+  // per-row scalars for limit rows are filled below by the owning dof lane
+  const int nscalar = nrow + nlim;
+  // ---- contact rows
+  int nefc = nscalar;
+  const int ncon = w->ncon;
+  for (int c = 0; c < ncon; c++) {
+    Contact* con = &w->con[c];
+    if (con->dist >= con->incl || nefc + con->dim > MW_MAXEFC) { if (lane == 0) con->row = -1; continue; }
+    int l1 = m->geom_link[con->g1], l2 = m->geom_link[con->g2];
+    unsigned m1 = l1 < 0 ? 0u : m->link_dofmask[l1], m2 = l2 < 0 ? 0u : m->link_dofmask[l2];
+    real p[3] = {con->pos[0], con->pos[1], con->pos[2]};
+    real jp1[3], jr1[3], jp2[3], jr2[3];
+    mw_jac_col(L, m1, lane, p, jp1, jr1);
+    mw_jac_col(L, m2, lane, p, jp2, jr2);
+    real dp[3], dr[3]; v3sub(dp, jp2, jp1); v3sub(dr, jr2, jr1);
+    if (lane < nv) {
+      for (int k = 0; k < 3; k++) J[(nefc + k) * NVP + lane] = v3dot(con->frame + 3 * k, dp);
+      if (con->dim > 3) J[(nefc + 3) * NVP + lane] = v3dot(con->frame, dr);
+    }
+    if (lane == 0) con->row = nefc;
+    nefc += con->dim;
+  }
+  SYNCW();
+  // ---- per-row scalars: weld (lanes 0..5), limits (owning dof lane), contacts (lane c)
+  if (lane < 6) {
+    real vel = 0; for (int k = 0; k < nv; k++) vel += J[lane * NVP + k] * w->qvel[k];
+    real sr[2] = {m->weld_solref[0], m->weld_solref[1]}, si[5] = {m->weld_solimp[0], m->weld_solimp[1], m->weld_solimp[2], m->weld_solimp[3], m->weld_solimp[4]};
+    RowParam rp = mw_impedance(cpos[lane], sr, si, h);
+    real diag = lane < 3 ? m->weld_invw[0] : m->weld_invw[1];
+    real Rr = fmax(MW_EPS, (1 - rp.imp) * diag / rp.imp);
+    w->eD[lane] = 1 / Rr;
+    w->eAref[lane] = -rp.B * vel - rp.K * rp.imp * cpos[lane];
+  }
+  if ((lim_lo || lim_hi) && myrank < nlim) {
+    int r = nrow + myrank;
+    real vel = (lim_lo ? (real)1 : (real)-1) * w->qvel[lane];
+    real sr[2] = {(real)0.02, (real)1}, si[5] = {(real)0.9, (real)0.95, (real)0.001, (real)0.5, (real)2};
+    RowParam rp = mw_impedance(ldist, sr, si, h);
+    real Rr = fmax(MW_EPS, (1 - rp.imp) * m->dof_invweight[lane] / rp.imp);
+    w->eD[r] = 1 / Rr;
+    w->eAref[r] = -rp.B * vel - rp.K * rp.imp * ldist;
+  }
+  if (lane < ncon && w->con[lane].row >= 0) {
+    Contact* con = &w->con[lane];
+    int r0 = con->row, dim = con->dim;
+    real tran = m->geom_invw[con->g1][0] + m->geom_invw[con->g2][0];
+    real rot = m->geom_invw[con->g1][1] + m->geom_invw[con->g2][1];
+    RowParam rp = mw_impedance(con->dist - con->incl, con->solref, con->solimp, h);
+    RowParam rf = mw_impedance((real)0, con->solref, con->solimp, h);
+    real R0 = fmax(MW_EPS, (1 - rp.imp) * tran / rp.imp);
+    (void)rot;
+    real R1 = R0 / m->impratio;
+    con->mu = con->fr1 * sqrt(R1 / R0);
+    real Rk[4] = {R0, R1, R1, R1 * con->fr1 * con->fr1 / (con->fr3 * con->fr3)};
+    for (int k = 0; k < dim; k++) {
+      real vel = 0; for (int d = 0; d < nv; d++) vel += J[(r0 + k) * NVP + d] * w->qvel[d];
+      w->eD[r0 + k] = 1 / Rk[k];
+      w->eAref[r0 + k] = k == 0 ? (-rp.B * vel - rp.K * rp.imp * (con->dist - con->incl)) : (-rf.B * vel);
+    }
+  }
+  if (lane == 0) { w->nefc = nefc; w->nscalar = nscalar; w->nweld = 6; }
+  SYNCW();
+}
+
+// ------------------------------------------------------------------ constraint cost / force / Hessian blocks
+// scalar rows on lanes [0,nscalar), contacts on lanes [0,ncon) (two passes); x = jar (+ alpha*jv).
+DEV real mw_scalar_row(const WarpScratch* w, int r, real x, real* f, real* hd) {
+  real D = w->eD[r];
+  bool active = (r < w->nweld) || x < 0;
+  *f = active ? -D * x : (real)0; *hd = active ? D : (real)0;
+  return active ? (real)0.5 * D * x * x : (real)0;
+}
+// elliptic cone block; x[0..dim) ; optionally forces and packed Hessian
+DEV real mw_cone(const WarpScratch* w, const Contact* con, const real* x, real* f, real* Hc, int* zone) {
+  const int r0 = con->row, dim = con->dim;
+  const real mu = con->mu;
+  real fr[4] = {0, con->fr1, con->fr1, con->fr3}, u[4] = {0, 0, 0, 0};
+  real N = x[0] * mu, T2 = 0;
+  for (int k = 1; k < dim; k++) { u[k] = x[k] * fr[k]; T2 += u[k] * u[k]; }
+  real T = sqrt(T2), cost = 0;
+  if (Hc) for (int i = 0; i < 10; i++) Hc[i] = 0;
+  if (N >= mu * T || (T <= 0 && N >= 0)) {
+    *zone = 0;
+    if (f) for (int k = 0; k < dim; k++) f[k] = 0;
+  } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
+    *zone = 1;
+    const int diag[4] = {0, 4, 7, 9};
+    for (int k = 0; k < dim; k++) {
+      real Dk = w->eD[r0 + k];
+      cost += (real)0.5 * Dk * x[k] * x[k];
+      if (f) f[k] = -Dk * x[k];
+      if (Hc) Hc[diag[k]] = Dk;
+    }
+  } else {
+    *zone = 2;
+    real Dm = w->eD[r0] / fmax(MW_EPS, mu * mu * (1 + mu * mu));
+    real NmT = N - mu * T;
+    cost = (real)0.5 * Dm * NmT * NmT;
+    real g[4] = {mu, 0, 0, 0};
+    for (int k = 1; k < dim; k++) g[k] = -mu * fr[k] * u[k] / T;
+    if (f) for (int k = 0; k < dim; k++) f[k] = -Dm * NmT * g[k];
+    if (Hc) {
+      real s = -Dm * NmT * mu, iT = 1 / T, iT3 = iT * iT * iT;
+      int idx = 0;
+      for (int a = 0; a < 4; a++) for (int b = a; b < 4; b++, idx++) {
+        if (a >= dim || b >= dim) continue;
+        real hv = Dm * g[a] * g[b];
+        if (a >= 1) { real t2 = -(fr[a] * u[a]) * (fr[b] * u[b]) * iT3; if (a == b) t2 += fr[a] * fr[a] * iT; hv += s * t2; }
+        Hc[idx] = hv;
+      }
+    }
+  }
+  return cost;
+}
+// full evaluation at jar: returns total constraint cost; stores forces (eF), scalar Hessian diag (eHd) and cone Hessians
+DEV real mw_constraint_eval(WarpScratch* w, int lane, bool want_hess) {
+  real cost = 0;
+  if (lane < w->nscalar) { real f, hd; cost += mw_scalar_row(w, lane, w->eJar[lane], &f, &hd); w->eF[lane] = f; w->eHd[lane] = hd; }
+  if (lane < w->ncon && w->con[lane].row >= 0) {
+    Contact* con = &w->con[lane];
+    real x[4] = {0, 0, 0, 0}, f[4]; int zone;
+    for (int k = 0; k < con->dim; k++) x[k] = w->eJar[con->row + k];
+    cost += mw_cone(w, con, x, f, want_hess ? con->H : nullptr, &zone);
+    for (int k = 0; k < con->dim; k++) w->eF[con->row + k] = f[k];
+    con->hzone = zone; con->fn = f[0];
+  }
+  return warp_sum(cost);
+}
+DEV void mw_linesearch_eval(const WarpScratch* w, int lane, real alpha, real* c, real* g, real* hh) {
+  real cc = 0, gg = 0, h2 = 0;
+  if (lane < w->nscalar) {
+    real jv = w->eJv[lane], x = w->eJar[lane] + alpha * jv, D = w->eD[lane];
+    if (lane < w->nweld || x < 0) { cc += (real)0.5 * D * x * x; gg += D * x * jv; h2 += D * jv * jv; }
+  }
+  if (lane < w->ncon && w->con[lane].row >= 0) {
+    const Contact* con = &w->con[lane];
+    const int r0 = con->row, dim = con->dim; const real mu = con->mu;
+    real fr[4] = {0, con->fr1, con->fr1, con->fr3};
+    real x0 = w->eJar[r0] + alpha * w->eJv[r0];
+    real N = x0 * mu, Np = w->eJv[r0] * mu, T2 = 0, xv = 0, vv = 0;
+    for (int k = 1; k < dim; k++) {
+      real fk = fr[k], jv = w->eJv[r0 + k], xk = w->eJar[r0 + k] + alpha * jv;
+      T2 += fk * fk * xk * xk; xv += fk * fk * xk * jv; vv += fk * fk * jv * jv;
+    }
+    real T = sqrt(T2);
+    if (N >= mu * T || (T <= 0 && N >= 0)) {
+    } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
+      for (int k = 0; k < dim; k++) {
+        real Dk = w->eD[r0 + k], jv = w->eJv[r0 + k], xk = w->eJar[r0 + k] + alpha * jv;
+        cc += (real)0.5 * Dk * xk * xk; gg += Dk * xk * jv; h2 += Dk * jv * jv;
+      }
+    } else {
+      real Dm = w->eD[r0] / fmax(MW_EPS, mu * mu * (1 + mu * mu));
+      real NmT = N - mu * T, Tp = xv / T, Tpp = vv / T - xv * xv / (T * T * T);
+      real r = Np - mu * Tp;
+      cc += (real)0.5 * Dm * NmT * NmT; gg += Dm * NmT * r; h2 += Dm * (r * r - NmT * mu * Tpp);
+    }
+  }
+  *c = warp_sum(cc); *g = warp_sum(gg); *hh = warp_sum(h2);
+}
+
+// y_lane = sum_k A[lane][k] x_k  (x published through vTmp)
+DEV real mw_matvec(const real* A, WarpScratch* w, real x, int nv, int lane) {
+  if (lane < nv) w->vTmp[lane] = x;
+  SYNCW();
+  real s = 0;
+  if (lane < nv) for (int k = 0; k < nv; k++) s += A[lane * NVP + k] * w->vTmp[k];
+  SYNCW();
+  return s;
+}
+// rows of J times a dof vector held in vTmp -> out[r]
+DEV void mw_J_times(const WarpScratch* w, const real* J, real* out, int nefc, int nv, int lane) {
+  for (int r = lane; r < nefc; r += 32) {
+    real s = 0;
+    for (int k = 0; k < nv; k++) s += J[r * NVP + k] * w->vTmp[k];
+    out[r] = s;
+  }
+}
+
+// ------------------------------------------------------------------ solver  [MuJoCo mj_solNewton, primal]
+// minimise 1/2 (a-a0)^T M (a-a0) + s(J a - aref).  Newton with exact Hessian + exact 1-D line search.
+__device__ __noinline__ void mw_solve(const MwModel* __restrict__ m, WarpScratch* w, int lane, int max_iter) {
+  real* J = w->U;
+  const int nv = m->nv, nefc = w->nefc;
+  const real scale = m->solver_scale;
+  const real tol = sizeof(real) == 4 ? (real)1e-7 : (real)1e-10;
+  const real qfs = lane < nv ? w->qfrc_smooth[lane] : (real)0;
+  const real a0 = lane < nv ? w->qacc_smooth[lane] : (real)0;
+  // ---- warm start selection  [mj_warmstart]
+  real qacc = 0, Ma = 0, cost = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    real a = lane < nv ? (pass == 0 ? w->warm[lane] : a0) : (real)0;
+    real Maa = mw_matvec(w->M, w, a, nv, lane);
+    if (lane < nv) w->vTmp[lane] = a;
+    SYNCW();
+    mw_J_times(w, J, w->eJar, nefc, nv, lane);
+    SYNCW();
+    for (int r = lane; r < nefc; r += 32) w->eJar[r] -= w->eAref[r];
+    SYNCW();
+    real gauss = warp_sum((real)0.5 * (a - a0) * (Maa - qfs));
+    real c = gauss + mw_constraint_eval(w, lane, false);
+    SYNCW();
+    if (pass == 0 || c < cost) { cost = c; qacc = a; Ma = Maa; if (pass == 1 || true) {} }
+    if (pass == 0) { /* keep jar of pass 0 only if it wins: recompute below */ }
+    else if (!(c <= cost)) { /* pass 1 lost: recompute jar for the warm start */ }
+  }
+  // recompute jar for the selected start (cheap, avoids branching on which pass won)
+  if (lane < nv) w->vTmp[lane] = qacc;
+  SYNCW();
+  mw_J_times(w, J, w->eJar, nefc, nv, lane);
+  SYNCW();
+  for (int r = lane; r < nefc; r += 32) w->eJar[r] -= w->eAref[r];
+  SYNCW();
+  int iter = 0;
+  for (; iter < max_iter; iter++) {
+    // forces + Hessian blocks at the current point
+    mw_constraint_eval(w, lane, true);
+    SYNCW();
+    // gradient
+    real grad = 0;
+    if (lane < nv) { grad = Ma - qfs; for (int r = 0; r < nefc; r++) grad -= J[r * NVP + lane] * w->eF[r]; }
+    real gn = sqrt(warp_sum(grad * grad));
+    if (scale * gn < tol) break;
+    // H = M + J^T Hblocks J : lane b owns column b, lower triangle a >= b
+    if (lane < nv) {
+      for (int a = lane; a < nv; a++) w->H[a * NVP + lane] = w->M[a * NVP + lane];
+      for (int r = 0; r < w->nscalar; r++) {
+        real hd = w->eHd[r];
+        if (hd == 0) continue;
+        real wb = hd * J[r * NVP + lane];
+        if (wb != 0) for (int a = lane; a < nv; a++) w->H[a * NVP + lane] += J[r * NVP + a] * wb;
+      }
+      for (int c = 0; c < w->ncon; c++) {
+        const Contact* con = &w->con[c];
+        if (con->row < 0 || con->hzone == 0) continue;
+        const int r0 = con->row, dim = con->dim;
+        real Jb[4], t[4];
+        for (int k = 0; k < dim; k++) Jb[k] = J[(r0 + k) * NVP + lane];
+        // t = Hc * Jb (packed symmetric upper, row-major 4x4)
+        const real* Hc = con->H;
+        const int ix[4][4] = {{0, 1, 2, 3}, {1, 4, 5, 6}, {2, 5, 7, 8}, {3, 6, 8, 9}};
+        for (int i = 0; i < dim; i++) { real s = 0; for (int k = 0; k < dim; k++) s += Hc[ix[i][k]] * Jb[k]; t[i] = s; }
+        for (int a = lane; a < nv; a++) { real s = 0; for (int k = 0; k < dim; k++) s += J[(r0 + k) * NVP + a] * t[k]; w->H[a * NVP + lane] += s; }
+      }
+    }
+    SYNCW();
+    mw_chol(w->H, nv, lane);
+    real search = -mw_chol_solve(w->H, grad, nv, lane);
+    real Ms = mw_matvec(w->M, w, search, nv, lane);
+    if (lane < nv) w->vTmp[lane] = search;
+    SYNCW();
+    mw_J_times(w, J, w->eJv, nefc, nv, lane);
+    SYNCW();
+    // exact line search (safeguarded Newton on a convex C1 function)
+    real c1 = warp_sum(search * (Ma - qfs)), c2 = warp_sum(search * Ms);
+    real cc, g1, g2;
+    mw_linesearch_eval(w, lane, 0, &cc, &g1, &g2);
+    real p1 = c1 + g1, p2 = c2 + g2;
+    if (!(p1 < 0)) break;
+    const real p10 = p1;
+    real lo = 0, hi = -1, alpha = -p1 / p2;
+    const real lstol = sizeof(real) == 4 ? (real)1e-5 : (real)1e-12;
+    for (int ls = 0; ls < 24; ls++) {
+      mw_linesearch_eval(w, lane, alpha, &cc, &g1, &g2);
+      p1 = c1 + alpha * c2 + g1; p2 = c2 + g2;
+      if (fabs(p1) < lstol * fabs(p10)) break;
+      if (p1 < 0) lo = alpha; else hi = alpha;
+      real an = alpha - p1 / p2;
+      if (hi > 0 && (an <= lo || an >= hi)) an = (real)0.5 * (lo + hi);
+      else if (hi < 0 && an <= lo) an = 2 * alpha;
+      if (an == alpha) break;
+      alpha = an;
+    }
+    qacc += alpha * search; Ma += alpha * Ms;
+    for (int r = lane; r < nefc; r += 32) w->eJar[r] += alpha * w->eJv[r];
+    SYNCW();
+    real gauss = warp_sum((real)0.5 * (qacc - a0) * (Ma - qfs));
+    real newcost = gauss + mw_constraint_eval(w, lane, false);
+    SYNCW();
+    real improvement = scale * (cost - newcost);
+    cost = newcost;
+    if (improvement < tol) { iter++; break; }
+  }
+  mw_constraint_eval(w, lane, false);
+  SYNCW();
+  real fc = 0;
+  if (lane < nv) { for (int r = 0; r < nefc; r++) fc += J[r * NVP + lane] * w->eF[r]; w->qacc[lane] = qacc; w->qfrc_con[lane] = fc; }
+  if (lane == 0) w->solver_iter = iter;
+  SYNCW();
+}
+
+// ------------------------------------------------------------------ forward dynamics + Euler
+// mj_forward  (positions -> qacc); leaves link poses / contacts / efc forces in the scratch.
+__device__ __noinline__ void mw_forward(const MwModel* __restrict__ m, const float* __restrict__ meshvert, WarpScratch* w, int lane) {
+  const int nv = m->nv;
+  mw_kinematics(m, w, lane);
+  LaneDof L; mw_lane_dof(m, w, lane, &L);
+  mw_mass_matrix(m, w, L, lane);
+  mw_collide(m, meshvert, w, lane);
+  mw_make_constraints(m, w, L, lane);
+  real bias = mw_rne_bias(m, w, L, lane);
+  // passive + actuation  [mj_passive, mj_fwdActuation]
+  real qfs = 0;
+  if (L.valid) {
+    real qv = w->qvel[lane];
+    qfs = -m->dof_damping[lane] * qv - bias;
+    real k = m->dof_stiffness[lane];
+    if (k != 0) qfs -= k * (w->qpos[m->dof_qadr[lane]] - m->dof_springref[lane]);
+    for (int u = 0; u < 2; u++) if (m->act_dof[u] == lane) {
+      real c = fmin(fmax(w->ctrl[u], (real)m->act_lo[u]), (real)m->act_hi[u]);
+      qfs += m->act_kp[u] * (c - w->qpos[m->dof_qadr[lane]]);
+    }
+    w->qfrc_smooth[lane] = qfs;
+  }
+  // qacc_smooth = M^-1 qfrc_smooth (factor in H)
+  for (int i = lane; i < nv * NVP; i += 32) w->H[i] = w->M[i];
+  SYNCW();
+  mw_chol(w->H, nv, lane);
+  real as = mw_chol_solve(w->H, qfs, nv, lane);
+  if (lane < nv) w->qacc_smooth[lane] = as;
+  SYNCW();
+  mw_solve(m, w, lane, sizeof(real) == 4 ? 8 : 50);
+}
+
+// mj_Euler: semi-implicit, joint damping implicit
+__device__ __noinline__ void mw_euler(const MwModel* __restrict__ m, WarpScratch* w, int lane) {
+  const int nv = m->nv; const real h = m->timestep;
+  for (int i = lane; i < nv * NVP; i += 32) w->H[i] = w->M[i];
+  SYNCW();
+  if (lane < nv) w->H[lane * NVP + lane] += h * m->dof_damping[lane];
+  SYNCW();
+  mw_chol(w->H, nv, lane);
+  real rhs = lane < nv ? w->qfrc_smooth[lane] + w->qfrc_con[lane] : (real)0;
+  real acc = mw_chol_solve(w->H, rhs, nv, lane);
+  if (lane < nv) { w->qvel[lane] += h * acc; w->warm[lane] = w->qacc[lane]; }
+  SYNCW();
+  // positions
+  if (lane < m->nlink) {
+    int l = lane, jt = m->link_jtype[l], qa = m->link_qadr[l], da = m->link_dadr[l];
+    if (jt == JT_FREE) {
+      for (int i = 0; i < 3; i++) w->qpos[qa + i] += h * w->qvel[da + i];
+      real wv[3] = {w->qvel[da + 3], w->qvel[da + 4], w->qvel[da + 5]};
+      real n = v3norm(wv);
+      if (n >= MW_EPS) {
+        real ax[3] = {wv[0] / n, wv[1] / n, wv[2] / n}, dq[4], q[4] = {w->qpos[qa + 3], w->qpos[qa + 4], w->qpos[qa + 5], w->qpos[qa + 6]}, r[4];
+        quat_axisangle(dq, ax, n * h);
+        quat_mul(r, q, dq); quat_normalize(r);
+        for (int i = 0; i < 4; i++) w->qpos[qa + 3 + i] = r[i];
+      }
+    } else w->qpos[qa] += h * w->qvel[da];
+  }
+  SYNCW();
+}

@@ -1,0 +1,202 @@
+"""ctypes binding of libmwb200.so (C ABI: include/metaworld_b200.h) over torch CUDA tensors.
+
+torch is only plumbing here: it owns device buffers and streams; all computation happens inside the
+CUDA library.  There is no CPU fallback: constructing an `Engine` without the built library or without a
+CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import lower, modelzoo
+from .tasks import TASKS, TaskSpec
+
+_LIB = None
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libmwb200.so")
+
+TASKCONST_DTYPE = np.dtype([("task_id", "i4"), ("nframe_task", "i4"), ("main_geom", "i4"), ("pad", "i4"),
+                            ("hand_init", "f4", 3), ("mocap_lo", "f4", 3), ("mocap_hi", "f4", 3),
+                            ("goal_lo", "f4", 3), ("goal_hi", "f4", 3), ("p", "f4", 16)])
+ENVSTATE_DTYPE = np.dtype([("qpos", "f4", 18), ("qvel", "f4", 17), ("warm", "f4", 17), ("mocap_pos", "f4", 3),
+                           ("prev_obs", "f4", 18), ("shift", "f4", 3), ("target", "f4", 3), ("obj_init", "f4", 3),
+                           ("init_tcp", "f4", 3), ("scal", "f4", 16), ("path_len", "f4"),
+                           ("partially_observable", "f4"), ("snapshot", "f4"), ("episode", "f4"), ("ep_return", "f4"),
+                           ("pad", "f4", 22)])
+SNAPSHOT_DTYPE = np.dtype([("st", ENVSTATE_DTYPE), ("obs", "f4", 39), ("pad", "f4", 25)])
+INFO_KEYS = ["success", "near_object", "grasp_success", "grasp_reward", "in_place_reward", "obj_to_target",
+             "unscaled_reward"]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(SO_PATH):
+            raise EngineError(f"{SO_PATH} is missing: build it with `python -m metaworld_b200.build` "
+                              "(the engine has no CPU fallback)")
+        L = C.CDLL(SO_PATH)
+        L.mw_last_error.restype = C.c_char_p
+        L.mw_build_info.restype = C.c_char_p
+        vp, ip = C.c_void_p, C.c_int
+        L.mw_create.argtypes = [C.POINTER(vp), ip, ip, vp, vp, C.POINTER(vp), vp]
+        L.mw_destroy.argtypes = [vp]
+        L.mw_set_envs.argtypes = [vp, ip, vp]
+        L.mw_build_snapshots.argtypes = [vp, ip, vp, vp, vp, vp]
+        L.mw_num_snapshots.argtypes = [vp]
+        L.mw_get_snapshots.argtypes = [vp, ip, ip, vp]
+        L.mw_reset.argtypes = [vp, ip, vp, vp, vp, ip, vp]
+        L.mw_step.argtypes = [vp, vp, vp, ip, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.mw_set_options.argtypes = [vp, ip, ip, C.c_ulonglong]
+        L.mw_set_goal_sets.argtypes = [vp, vp, vp]
+        L.mw_get_state.argtypes = [vp, vp]
+        L.mw_set_state.argtypes = [vp, vp]
+        L.mw_debug_substeps.argtypes = [vp, ip, vp, vp]
+        L.mw_get_counters.argtypes = [vp, vp]
+        assert L.mw_sizeof_model() == lower.DTYPE.itemsize, "MwModel layout mismatch (rebuild the library)"
+        assert L.mw_sizeof_taskconst() == TASKCONST_DTYPE.itemsize
+        assert L.mw_sizeof_envstate() == ENVSTATE_DTYPE.itemsize == 512
+        assert L.mw_sizeof_snapshot() == SNAPSHOT_DTYPE.itemsize == 768
+        _LIB = L
+    return _LIB
+
+
+def _ck(rc):
+    if rc != 0:
+        raise EngineError(lib().mw_last_error().decode() or f"libmwb200 error {rc}")
+
+
+_LOWERED: dict = {}
+
+
+def lowered(spec: TaskSpec) -> lower.Lowered:
+    if spec.name not in _LOWERED:
+        m = modelzoo.full_model(spec.xml)
+        _LOWERED[spec.name] = lower.lower(m, spec.movable, spec.frames)
+    return _LOWERED[spec.name]
+
+
+def task_const(spec: TaskSpec, lw: lower.Lowered) -> np.ndarray:
+    tc = np.zeros((), dtype=TASKCONST_DTYPE)
+    tc["task_id"] = spec.task_id
+    tc["nframe_task"] = len(spec.frames)
+    tc["main_geom"] = lw.geom_names.index(spec.main_geom) if spec.main_geom in lw.geom_names else -1
+    tc["hand_init"] = spec.hand_init_pos
+    tc["mocap_lo"], tc["mocap_hi"] = spec.hand_low, spec.hand_high
+    tc["goal_lo"], tc["goal_hi"] = spec.goal_low, spec.goal_high
+    p = np.zeros(16, dtype=np.float32)
+    p[: len(spec.params)] = spec.params
+    # collider slots of the two finger pads (touching_object, sawyer_xyz_env.py:401-440)
+    p[14] = lw.geom_names.index("leftpad_geom")
+    p[15] = lw.geom_names.index("rightpad_geom")
+    tc["p"] = p
+    return tc
+
+
+class Engine:
+    """One engine per process / GPU.  `task_names[i]` defines model slot i."""
+
+    def __init__(self, task_names, device=0):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise EngineError("CUDA device required: metaworld_b200 has no CPU execution path")
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        self.specs = [TASKS[n] for n in task_names]
+        self.lowered = [lowered(s) for s in self.specs]
+        models = np.stack([lw.rec for lw in self.lowered])
+        tcs = np.stack([task_const(s, lw) for s, lw in zip(self.specs, self.lowered)])
+        self._mesh = [np.ascontiguousarray(lw.meshvert, dtype=np.float32) for lw in self.lowered]
+        ptrs = (C.c_void_p * len(self._mesh))(*[m.ctypes.data if len(m) else None for m in self._mesh])
+        nmv = np.array([len(m) for m in self._mesh], dtype=np.int32)
+        self.h = C.c_void_p()
+        _ck(lib().mw_create(C.byref(self.h), device, len(self.specs), models.ctypes.data, tcs.ctypes.data, ptrs,
+                            nmv.ctypes.data))
+        self.n_envs = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().mw_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_envs(self, env_model):
+        em = np.ascontiguousarray(env_model, dtype=np.int32)
+        _ck(lib().mw_set_envs(self.h, len(em), em.ctypes.data))
+        self.n_envs = len(em)
+        self.env_model = em
+
+    def set_options(self, max_episode_steps=500, terminate_on_success=False, seed=0):
+        _ck(lib().mw_set_options(self.h, int(max_episode_steps), int(bool(terminate_on_success)), int(seed) & (2**64 - 1)))
+
+    def build_snapshots(self, model_idx, rand_vec, partially_observable):
+        mi = np.ascontiguousarray(model_idx, dtype=np.int32)
+        rv = np.zeros((len(mi), 6), dtype=np.float32)
+        rand_vec = np.asarray(rand_vec, dtype=np.float64).reshape(len(mi), -1)
+        rv[:, : rand_vec.shape[1]] = rand_vec
+        po = np.ascontiguousarray(partially_observable, dtype=np.uint8)
+        ids = np.zeros(len(mi), dtype=np.int32)
+        _ck(lib().mw_build_snapshots(self.h, len(mi), mi.ctypes.data, rv.ctypes.data, po.ctypes.data, ids.ctypes.data))
+        return ids
+
+    def get_snapshots(self, first=0, n=None):
+        n = lib().mw_num_snapshots(self.h) - first if n is None else n
+        out = np.zeros(n, dtype=SNAPSHOT_DTYPE)
+        _ck(lib().mw_get_snapshots(self.h, first, n, out.ctypes.data))
+        return out
+
+    def set_goal_sets(self, first, count):
+        f = np.ascontiguousarray(first, dtype=np.int32)
+        c = np.ascontiguousarray(count, dtype=np.int32)
+        _ck(lib().mw_set_goal_sets(self.h, f.ctypes.data, c.ctypes.data))
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def reset(self, snapshot_ids, obs, env_ids=None):
+        n = snapshot_ids.numel()
+        _ck(lib().mw_reset(self.h, n, self._p(env_ids), self._p(snapshot_ids), self._p(obs), obs.stride(0), self._stream()))
+
+    def step(self, actions, obs, reward, terminated, truncated, info, final_obs=None, final_info=None, next_snapshot=None):
+        _ck(lib().mw_step(self.h, self._p(actions), self._p(obs), obs.stride(0), self._p(reward), self._p(terminated),
+                          self._p(truncated), self._p(info), self._p(final_obs), self._p(final_info),
+                          self._p(next_snapshot), self._stream()))
+
+    def get_state(self):
+        out = np.zeros(self.n_envs, dtype=ENVSTATE_DTYPE)
+        self.torch.cuda.synchronize(self.device)
+        _ck(lib().mw_get_state(self.h, out.ctypes.data))
+        return out
+
+    def set_state(self, st):
+        st = np.ascontiguousarray(st, dtype=ENVSTATE_DTYPE)
+        assert len(st) == self.n_envs
+        self.torch.cuda.synchronize(self.device)
+        _ck(lib().mw_set_state(self.h, st.ctypes.data))
+
+    def debug_substeps(self, nstep, ctrl=(0.0, 0.0)):
+        c = np.array(ctrl, dtype=np.float32)
+        _ck(lib().mw_debug_substeps(self.h, int(nstep), c.ctypes.data, self._stream()))
+
+    def counters(self):
+        out = np.zeros(5, dtype=np.uint64)
+        self.torch.cuda.synchronize(self.device)
+        _ck(lib().mw_get_counters(self.h, out.ctypes.data))
+        return dict(launches=int(out[0]), env_steps=int(out[1]), contacts_dropped=int(out[2]),
+                    solver_iters=int(out[3]), forward_passes=int(out[4]))
