@@ -1,0 +1,124 @@
+"""Benchmark definitions and task (goal) generation -- host side, run once at construction.
+
+Mirrors the reference's registration layer: ``metaworld/env_dict.py`` (which env names make up
+MT10/MT25/MT50 and the ML10/ML25/ML45 train/test splits; the order defines env ids / one-hot ids)
+and ``metaworld/__init__.py:114-179`` (`_make_tasks`: the exact NumPy legacy-RNG protocol that turns a
+seed into 50 goal vectors per env class).  `Task` keeps the reference's data format
+(``metaworld/types.py:10-17``: env_name + pickled dict).
+"""
+from __future__ import annotations
+
+import pickle
+from dataclasses import dataclass
+
+import numpy as np
+
+from .tasks import TASKS
+
+N_GOALS = 50  # metaworld/__init__.py:97
+
+ALL_V3 = [
+    "assembly-v3", "basketball-v3", "bin-picking-v3", "box-close-v3", "button-press-topdown-v3",
+    "button-press-topdown-wall-v3", "button-press-v3", "button-press-wall-v3", "coffee-button-v3", "coffee-pull-v3",
+    "coffee-push-v3", "dial-turn-v3", "disassemble-v3", "door-close-v3", "door-lock-v3", "door-open-v3",
+    "door-unlock-v3", "hand-insert-v3", "drawer-close-v3", "drawer-open-v3", "faucet-open-v3", "faucet-close-v3",
+    "hammer-v3", "handle-press-side-v3", "handle-press-v3", "handle-pull-side-v3", "handle-pull-v3", "lever-pull-v3",
+    "pick-place-wall-v3", "pick-out-of-hole-v3", "pick-place-v3", "plate-slide-v3", "plate-slide-side-v3",
+    "plate-slide-back-v3", "plate-slide-back-side-v3", "peg-insert-side-v3", "peg-unplug-side-v3", "soccer-v3",
+    "stick-push-v3", "stick-pull-v3", "push-v3", "push-wall-v3", "push-back-v3", "reach-v3", "reach-wall-v3",
+    "shelf-place-v3", "sweep-into-v3", "sweep-v3", "window-open-v3", "window-close-v3",
+]
+MT10 = ["reach-v3", "push-v3", "pick-place-v3", "door-open-v3", "drawer-open-v3", "drawer-close-v3",
+        "button-press-topdown-v3", "peg-insert-side-v3", "window-open-v3", "window-close-v3"]
+MT25 = MT10 + ["coffee-pull-v3", "pick-out-of-hole-v3", "disassemble-v3", "pick-place-wall-v3", "basketball-v3",
+               "stick-pull-v3", "button-press-wall-v3", "faucet-open-v3", "door-lock-v3", "lever-pull-v3",
+               "sweep-into-v3", "faucet-close-v3", "coffee-button-v3", "button-press-topdown-wall-v3", "dial-turn-v3"]
+MT50 = list(ALL_V3)
+ML10 = dict(train=["reach-v3", "push-v3", "pick-place-v3", "door-open-v3", "drawer-close-v3", "button-press-topdown-v3",
+                   "peg-insert-side-v3", "window-open-v3", "sweep-v3", "basketball-v3"],
+            test=["drawer-open-v3", "door-close-v3", "shelf-place-v3", "sweep-into-v3", "lever-pull-v3"])
+ML25 = dict(train=list(MT25), test=["basketball-v3", "door-close-v3", "shelf-place-v3", "sweep-v3", "button-press-v3"])
+ML45 = dict(train=["assembly-v3", "basketball-v3", "button-press-topdown-v3", "button-press-topdown-wall-v3",
+                   "button-press-v3", "button-press-wall-v3", "coffee-button-v3", "coffee-pull-v3", "coffee-push-v3",
+                   "dial-turn-v3", "disassemble-v3", "door-close-v3", "door-open-v3", "drawer-close-v3",
+                   "drawer-open-v3", "faucet-open-v3", "faucet-close-v3", "hammer-v3", "handle-press-side-v3",
+                   "handle-press-v3", "handle-pull-side-v3", "handle-pull-v3", "lever-pull-v3", "pick-place-wall-v3",
+                   "pick-out-of-hole-v3", "push-back-v3", "pick-place-v3", "plate-slide-v3", "plate-slide-side-v3",
+                   "plate-slide-back-v3", "plate-slide-back-side-v3", "peg-insert-side-v3", "peg-unplug-side-v3",
+                   "soccer-v3", "stick-push-v3", "stick-pull-v3", "push-wall-v3", "push-v3", "reach-wall-v3",
+                   "reach-v3", "shelf-place-v3", "sweep-into-v3", "sweep-v3", "window-open-v3", "window-close-v3"],
+            test=["bin-picking-v3", "box-close-v3", "hand-insert-v3", "door-lock-v3", "door-unlock-v3"])
+
+
+@dataclass
+class Task:
+    """Same shape as the reference's ``metaworld.types.Task``: ``data`` is a pickled dict with
+    ``rand_vec``, ``env_cls`` (here: the env name string) and ``partially_observable``."""
+    env_name: str
+    data: bytes
+
+    def unpack(self):
+        return pickle.loads(self.data)
+
+
+def draw_rand_vec(spec, rs: np.random.RandomState):
+    """One ``reset_model`` worth of ``_get_state_rand_vec`` calls with ``_freeze_rand_vec=False``
+    (sawyer_xyz_env.py:709-719 + the task's rejection loop, e.g. sawyer_reach_v3.py:125-129)."""
+    lo, hi = spec.rand_low, spec.rand_high
+    v = rs.uniform(lo, hi, size=lo.size).astype(np.float64)
+    if spec.reject is not None:
+        (a0, a1), (b0, b1), thr = spec.reject
+        while np.linalg.norm(v[a0:a1] - v[b0:b1]) < thr:
+            v = rs.uniform(lo, hi, size=lo.size).astype(np.float64)
+    return v
+
+
+def make_tasks(env_names, partially_observable: bool, seed=None, n_goals=N_GOALS):
+    """``_make_tasks`` (metaworld/__init__.py:114-179): per env class, ``n_goals`` resets with an unfrozen
+    rand_vec; every reset runs ``reset_model`` twice (sawyer_xyz_env.py:677-678) so two draws happen per goal
+    and the second one is kept."""
+    rs = np.random.RandomState(seed) if seed is not None else np.random.RandomState()
+    tasks = []
+    for name in env_names:
+        spec = TASKS[name]
+        vecs = []
+        for _ in range(n_goals):
+            draw_rand_vec(spec, rs)           # pass 1 (discarded)
+            vecs.append(draw_rand_vec(spec, rs))  # pass 2
+        if len(np.unique(np.array(vecs), axis=0)) != n_goals:
+            raise AssertionError(f"Only generated {len(np.unique(np.array(vecs), axis=0))} unique goals, not {n_goals}")
+        for v in vecs:
+            tasks.append(Task(name, pickle.dumps(dict(rand_vec=v, env_cls=name, partially_observable=partially_observable))))
+    return tasks
+
+
+class Benchmark:
+    """``metaworld.Benchmark`` surface: train_classes / test_classes (name lists) and train_tasks / test_tasks."""
+
+    def __init__(self, train, test, partially_observable, seed, test_seed=None):
+        self.train_classes = list(train)
+        self.test_classes = list(test)
+        self.train_tasks = make_tasks(train, partially_observable, seed)
+        self.test_tasks = make_tasks(test, partially_observable, seed if test_seed is None else test_seed) if test else []
+
+
+def MT1(env_name, seed=None):
+    b = Benchmark([env_name], [], False, seed)
+    b.test_classes = [env_name]
+    return b
+
+
+def ML1(env_name, seed=None):
+    return Benchmark([env_name], [env_name], True, seed, test_seed=(seed + 1 if seed is not None else None))
+
+
+def make_benchmark(name, seed=None):
+    if name in TASKS or name in ALL_V3:
+        return MT1(name, seed)
+    table = dict(MT10=(MT10, [], False), MT25=(MT25, [], False), MT50=(MT50, [], False),
+                 ML10=(ML10["train"], ML10["test"], True), ML25=(ML25["train"], ML25["test"], True),
+                 ML45=(ML45["train"], ML45["test"], True))
+    if name not in table:
+        raise ValueError(f"unknown benchmark {name!r}")
+    tr, te, po = table[name]
+    return Benchmark(tr, te, po, seed)

@@ -175,9 +175,13 @@ DEV void seg_box_min(const real* p0, const real* dir, const real* size, real* tl
       if (x > size[i] || x < -size[i]) { real aa = p0[i] + (x > size[i] ? -size[i] : size[i]), bb = dir[i]; A += bb * bb; B += 2 * aa * bb; C += aa * aa; }
     }
     real tl, th, f;
-    if (A < (real)1e-20) { tl = t0; th = t1; f = C; }
-    else { real ts = fmin(fmax(-B / (2 * A), t0), t1); tl = th = ts; f = A * ts * ts + B * ts + C; }
-    real tol = (real)1e-12;
+    real f0 = A * t0 * t0 + B * t0 + C, f1 = A * t1 * t1 + B * t1 + C;
+    real ts = A > 0 ? fmin(fmax(-B / (2 * A), t0), t1) : t0;
+    f = A * ts * ts + B * ts + C;
+    const real rel = sizeof(real) == 4 ? (real)1e-5 : (real)1e-9;
+    if (fmax(f0, f1) - f <= rel * f + (real)1e-18) { tl = t0; th = t1; f = fmin(fmin(f0, f1), f); }   // flat: segment parallel to the face
+    else { tl = th = ts; }
+    real tol = rel * best + (real)1e-18;
     if (f < best - tol) { best = f; blo = tl; bhi = th; }
     else if (fabs(f - best) <= tol && tl <= bhi + (real)1e-6) { if (th > bhi) bhi = th; }
   }
@@ -468,6 +472,31 @@ DEV bool epa_add_face(EpaWs* W, int* nf, int a, int b, int c) {
   return true;
 }
 
+
+// Face-on contact of a cylinder cap with a box face: every point of the overlap patch is a valid EPA witness, so the
+// contact point is implementation-defined.  We take the pressure centroid of the (linearly penetrating) cap: offset
+// r^2 sin(tilt) / (4 p0) from the cap centre towards the deepest rim point (p0 = penetration of the cap centre),
+// clamped to the rim.  Every other configuration is left untouched.
+DEV void refine_cyl_box(const DShape& A, const DShape& B, RawCon* o) {
+  if (A.type != G_CYLINDER || B.type != G_BOX) return;
+  real nl[3], nb[3]; mat_tmulvec(nl, A.mat, o->normal); mat_tmulvec(nb, B.mat, o->normal);
+  if (fabs(nl[2]) < (real)0.9) return;
+  int k = 0; for (int i = 1; i < 3; i++) if (fabs(nb[i]) > fabs(nb[k])) k = i;
+  if (fabs(nb[k]) < (real)0.99999) return;
+  real r = A.size[0], depth = -o->dist, rad = sqrt(nl[0] * nl[0] + nl[1] * nl[1]);
+  real p0 = depth - r * rad;
+  if (p0 <= 0) return;
+  real sbar = rad > (real)1e-12 ? fmin(r, r * r * rad / (4 * p0)) : (real)0;
+  real pl[3] = {0, 0, nl[2] > 0 ? A.size[1] : -A.size[1]}, pw[3], t[3], pb[3];
+  if (rad > (real)1e-12) { pl[0] = nl[0] / rad * sbar; pl[1] = nl[1] / rad * sbar; }
+  mat_mulvec(pw, A.mat, pl); v3add(pw, pw, A.pos);
+  v3sub(t, pw, B.pos); mat_tmulvec(pb, B.mat, t);
+  for (int i = 0; i < 3; i++) if (i != k && fabs(pb[i]) > B.size[i]) return;
+  real pen = p0 + sbar * rad;
+  o->dist = -pen;
+  v3addscl(o->pos, pw, o->normal, (real)-0.5 * pen);
+}
+
 // Whole warp calls this with identical A, B.  The result (count 0/1, contact in *o) is valid on every lane.
 __device__ __noinline__ int convex_pair(const DShape& A, const DShape& B, real margin, RawCon* o, EpaWs* W, int lane) {
   const real dirs[6][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1}};
@@ -607,6 +636,7 @@ __device__ __noinline__ int convex_pair(const DShape& A, const DShape& B, real m
       if (dist <= margin) {
         rc.dist = dist; v3copy(rc.normal, f->n);
         for (int q = 0; q < 3; q++) rc.pos[q] = (real)0.5 * (wa[q] + rc.normal[q] * ra + wb[q] - rc.normal[q] * rb);
+        refine_cyl_box(A, B, &rc);
         result = 1;
       }
     }

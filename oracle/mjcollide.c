@@ -213,10 +213,13 @@ static double seg_box_min(const double* p0, const double* dir, const double* siz
       if (x > size[i] || x < -size[i]) { double a = p0[i] + off, b = dir[i]; A += b * b; B += 2 * a * b; C += a * a; }
     }
     double tl, th, f;
-    if (A < 1e-300) { tl = t0; th = t1; f = C; }
-    else { double ts = -B / (2 * A); if (ts < t0) ts = t0; if (ts > t1) ts = t1; tl = th = ts; f = A * ts * ts + B * ts + C; }
-    if (f < best - 1e-18) { best = f; blo = tl; bhi = th; }
-    else if (fabs(f - best) <= 1e-18 && tl <= bhi + 1e-12) { if (th > bhi) bhi = th; }
+    double f0 = A * t0 * t0 + B * t0 + C, f1 = A * t1 * t1 + B * t1 + C;
+    double ts = A > 0 ? -B / (2 * A) : t0; if (ts < t0) ts = t0; if (ts > t1) ts = t1;
+    f = A * ts * ts + B * ts + C;
+    if (fmax(f0, f1) - f <= 1e-9 * f + 1e-18) { tl = t0; th = t1; f = fmin(f0, f1) < f ? fmin(f0, f1) : f; } /* flat: segment parallel to the face */
+    else { tl = th = ts; }
+    if (f < best - (1e-9 * best + 1e-18)) { best = f; blo = tl; bhi = th; }
+    else if (fabs(f - best) <= 1e-9 * best + 1e-18 && tl <= bhi + 1e-12) { if (th > bhi) bhi = th; }
   }
   *tlo = blo; *thi = bhi;
   return best;
@@ -561,6 +564,31 @@ static int epa(const Shape* A, const Shape* B, SV* s, int n, RawCon* o, double* 
   return 1;
 }
 
+
+/* Face-on contact of a cylinder cap with a box face: every point of the overlap patch is a valid EPA witness, so
+   the contact point is implementation-defined.  We take the pressure centroid of the (linearly penetrating) cap:
+   offset r^2 sin(tilt) / (4 p0) from the cap centre towards the deepest rim point (p0 = penetration of the cap
+   centre), clamped to the rim.  Leaves every other configuration untouched. */
+static void refine_cyl_box(const Shape* A, const Shape* B, RawCon* o) {
+  if (A->type != G_CYLINDER || B->type != G_BOX) return;
+  double nl[3], nb[3]; mat_tmulvec(nl, A->mat, o->normal); mat_tmulvec(nb, B->mat, o->normal);
+  if (fabs(nl[2]) < 0.9) return;
+  int k = 0; for (int i = 1; i < 3; i++) if (fabs(nb[i]) > fabs(nb[k])) k = i;
+  if (fabs(nb[k]) < 0.99999) return;
+  double r = A->size[0], depth = -o->dist, rad = sqrt(nl[0] * nl[0] + nl[1] * nl[1]);
+  double p0 = depth - r * rad;
+  if (p0 <= 0) return;
+  double sbar = rad > 1e-12 ? fmin(r, r * r * rad / (4 * p0)) : 0.0;
+  double pl[3] = {0, 0, nl[2] > 0 ? A->size[1] : -A->size[1]}, pw[3], t[3], pb[3];
+  if (rad > 1e-12) { pl[0] = nl[0] / rad * sbar; pl[1] = nl[1] / rad * sbar; }
+  mat_mulvec(pw, A->mat, pl); v3add(pw, pw, A->pos);
+  v3sub(t, pw, B->pos); mat_tmulvec(pb, B->mat, t);
+  for (int i = 0; i < 3; i++) if (i != k && fabs(pb[i]) > B->size[i]) return;
+  double pen = p0 + sbar * rad;
+  o->dist = -pen;
+  v3addscl(o->pos, pw, o->normal, -0.5 * pen);
+}
+
 static int convex_convex(const Shape* A, const Shape* B, double margin, RawCon* o) {
   SV s[4]; int n = 0;
   double v[3]; v3sub(v, A->pos, B->pos);
@@ -607,6 +635,7 @@ static int convex_convex(const Shape* A, const Shape* B, double margin, RawCon* 
   o->dist = dist; v3copy(o->normal, r.normal);
   double sa[3], sb[3]; v3addscl(sa, wa, o->normal, ra); v3addscl(sb, wb, o->normal, -rb);
   for (int k = 0; k < 3; k++) o->pos[k] = 0.5 * (sa[k] + sb[k]);
+  refine_cyl_box(A, B, o);
   return 1;
 }
 

@@ -1,0 +1,214 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI (metaworld_b200.engine -> libmwb200.so), against
+(a) committed oracle golden trajectories (tests/golden/traj_*.npz), (b) the live CPU oracle on fresh seeds and
+(c) size-independent properties at the benchmark's full size (4096 envs).
+
+Tolerances (float32 device vs float64 oracle): 1e-4 absolute on observations and rewards, as BASELINE.json's
+north_star states; success flags must be equal.  PARITY UNPINNED w.r.t. MuJoCo itself (see oracle/mjphys.h)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-4
+
+
+def _tasks_with_goldens():
+    from metaworld_b200.tasks import TASKS
+    names = [os.path.basename(p)[5:-4] for p in sorted(glob.glob(os.path.join(GOLD, "traj_*.npz")))]
+    return [n for n in names if n in TASKS]
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+class Rig:
+    """N envs of one task, driven through the raw engine (C ABI)."""
+
+    def __init__(self, torch, task, rand_vecs, partial=False):
+        from metaworld_b200.engine import Engine
+        self.t = torch
+        self.eng = Engine([task])
+        n = len(rand_vecs)
+        self.ids = self.eng.build_snapshots([0] * n, rand_vecs, [int(partial)] * n)
+        self.eng.set_envs([0] * n)
+        self.eng.set_options(500, False, 0)
+        d = self.eng.device
+        self.n = n
+        self.obs = torch.zeros(n, 39, device=d); self.rew = torch.zeros(n, device=d)
+        self.term = torch.zeros(n, dtype=torch.uint8, device=d); self.trunc = torch.zeros(n, dtype=torch.uint8, device=d)
+        self.info = torch.zeros(n, 7, device=d); self.fobs = torch.zeros(n, 39, device=d); self.finfo = torch.zeros(n, 8, device=d)
+        self.sid = torch.tensor(self.ids, dtype=torch.int32, device=d)
+
+    def reset(self):
+        self.eng.reset(self.sid, self.obs)
+        return self.obs.cpu().numpy()
+
+    def step(self, a):
+        self.eng.step(self.t.tensor(np.ascontiguousarray(a, dtype=np.float32), device=self.eng.device), self.obs, self.rew, self.term,
+                      self.trunc, self.info, self.fobs, self.finfo, self.sid)
+        return self.obs.cpu().numpy(), self.rew.cpu().numpy(), self.info.cpu().numpy(), self.term.cpu().numpy(), self.trunc.cpu().numpy()
+
+
+@pytest.mark.parametrize("task", _tasks_with_goldens())
+def test_reset_snapshot_matches_golden(torch_cuda, task):
+    g = np.load(os.path.join(GOLD, f"traj_{task}.npz"))
+    rig = Rig(torch_cuda, task, g["rand_vec"])
+    snaps = rig.eng.get_snapshots()
+    nq, nv = g["reset_qpos"].shape[1], g["reset_qvel"].shape[1]
+    for k in range(rig.n):
+        assert np.abs(snaps[k]["obs"] - g["reset_obs"][k]).max() < TOL
+        assert np.abs(snaps[k]["st"]["qpos"][:nq] - g["reset_qpos"][k]).max() < TOL
+        assert np.abs(snaps[k]["st"]["qvel"][:nv] - g["reset_qvel"][k]).max() < 1e-3
+    assert np.array_equal(rig.reset(), np.stack([s["obs"] for s in snaps]))
+
+
+@pytest.mark.parametrize("task", _tasks_with_goldens())
+def test_open_loop_rollout_matches_golden(torch_cuda, task):
+    g = np.load(os.path.join(GOLD, f"traj_{task}.npz"))
+    rig = Rig(torch_cuda, task, g["rand_vec"])
+    rig.reset()
+    T = g["actions"].shape[1]
+    worst_o = worst_r = 0.0
+    for t in range(T):
+        o, r, info, term, trunc = rig.step(g["actions"][:, t])
+        worst_o = max(worst_o, np.abs(o - g["obs"][:, t]).max())
+        worst_r = max(worst_r, np.abs(r - g["reward"][:, t]).max())
+        assert np.array_equal(info[:, 0], g["success"][:, t])
+    print(f"{task}: open-loop {T} steps worst obs err {worst_o:.2e} reward err {worst_r:.2e}")
+    assert worst_o < TOL and worst_r < TOL
+
+
+@pytest.mark.parametrize("task", _tasks_with_goldens())
+def test_teacher_forced_one_step(torch_cuda, task):
+    """From oracle states (qpos, qvel, mocap, prev obs) one device step must land on the oracle's next step."""
+    g = np.load(os.path.join(GOLD, f"traj_{task}.npz"))
+    rig = Rig(torch_cuda, task, g["rand_vec"])
+    rig.reset()
+    nq, nv = g["qpos"].shape[2], g["qvel"].shape[2]
+    worst = 0.0
+    for t in range(0, g["actions"].shape[1] - 1, 7):
+        st = rig.eng.get_state()
+        for k in range(rig.n):
+            st[k]["qpos"][:nq] = g["qpos"][k, t]; st[k]["qvel"][:nv] = g["qvel"][k, t]
+            st[k]["mocap_pos"] = g["mocap"][k, t]; st[k]["prev_obs"] = g["obs"][k, t][:18]
+            st[k]["warm"][:] = 0; st[k]["path_len"] = t + 1
+        rig.eng.set_state(st)
+        o, r, info, _, _ = rig.step(g["actions"][:, t + 1])
+        worst = max(worst, np.abs(o - g["obs"][:, t + 1]).max(), np.abs(r - g["reward"][:, t + 1]).max())
+    print(f"{task}: teacher-forced worst err {worst:.2e}")
+    assert worst < TOL
+
+
+def test_live_oracle_fresh_seed(torch_cuda):
+    """Not a fixture: a goal and an action sequence the goldens never saw."""
+    from oracle.tasks import TASKS as OT
+    from metaworld_b200 import benchmarks as B
+    for task in _tasks_with_goldens()[:3]:
+        rv = B.make_tasks([task], False, seed=9001, n_goals=1)[0].unpack()["rand_vec"]
+        rig = Rig(torch_cuda, task, [np.pad(rv, (0, 6 - len(rv)))])
+        oe = OT[task](); oe.set_task_vec(rv, False)
+        oo, _ = oe.reset()
+        assert np.abs(rig.reset()[0] - oo).max() < TOL
+        rng = np.random.default_rng(77)
+        for t in range(25):
+            a = rng.uniform(-1, 1, 4).astype(np.float32)
+            o, r, info, _, _ = rig.step(a[None])
+            oo, orr, _, _, oi = oe.step(a)
+            assert np.abs(o[0] - oo).max() < TOL and abs(r[0] - orr) < TOL and info[0, 0] == oi["success"]
+
+
+def test_bitwise_determinism(torch_cuda):
+    from metaworld_b200 import benchmarks as B
+    rvs = [t.unpack()["rand_vec"] for t in B.make_tasks(["reach-v3"], False, seed=1, n_goals=8)]
+    outs = []
+    for rep in range(2):
+        rig = Rig(torch_cuda, "reach-v3", rvs)
+        rig.reset()
+        rng = np.random.default_rng(5)
+        for _ in range(20):
+            o, r, info, _, _ = rig.step(rng.uniform(-1, 1, (8, 4)))
+        outs.append((o.copy(), r.copy(), rig.eng.get_state()["qpos"].copy()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
+
+
+def test_vector_env_api_and_autoreset(torch_cuda):
+    from metaworld_b200.vector_env import make_mt_envs
+    env = make_mt_envs("reach-v3", seed=42, num_envs=6, max_episode_steps=7, use_one_hot=True, num_tasks=3)
+    assert env.num_envs == 6 and env.single_observation_space.shape == (42,) and env.single_action_space.shape == (4,)
+    obs, info = env.reset()
+    assert obs.shape == (6, 42) and obs.dtype == np.float32 and np.all(obs[:, 39] == 1) and np.all(obs[:, 40:] == 0)
+    assert np.all(obs[:, 36:39] != 0)                                   # MT: goal observable (test_new_api.py:212)
+    assert env.get_attr("task_name") == tuple(["reach-v3"] * 6) and len(env.get_attr("tasks")[0]) == 50
+    rv0 = np.array(env.get_attr("_last_rand_vec"))
+    first = obs.copy()
+    for t in range(7):
+        prev = obs
+        obs, rew, term, trunc, infos = env.step(env.action_space.sample())
+        assert obs.shape == (6, 42) and rew.dtype == np.float64 and term.dtype == bool and trunc.dtype == bool
+        if t < 6:
+            assert not trunc.any() and np.allclose(obs[:, 18:36], prev[:, :18], atol=0)   # tests/helpers.py:33
+    assert trunc.all() and not term.any()                              # TimeLimit at max_episode_steps
+    assert "final_obs" in infos and infos["_final_obs"].all() and infos["final_info"]["episode"]["l"].tolist() == [7] * 6
+    assert np.all(infos["final_info"]["episode"]["r"] > 0)
+    # SAME_STEP autoreset: the returned obs is the reset obs of the (re-sampled) task
+    rv1 = np.array(env.get_attr("_last_rand_vec"))
+    assert not np.array_equal(rv0, rv1) and np.allclose(obs[:, 18:36], obs[:, :18])
+    assert np.allclose(np.stack(infos["final_obs"])[:, 18:36], prev[:, :18])
+    # replicas 0 (envs 0..) share the seed -> identical task streams, replica seeds differ by +1 per replica
+    env.call("toggle_terminate_on_success", True)
+    assert env.get_attr("terminate_on_success") == tuple([True] * 6)
+    ck = env.call("get_checkpoint"); env.call("load_checkpoint", ck)
+    with pytest.raises(AttributeError):
+        env.get_attr("nonexistent")
+    env.close()
+
+
+def test_ml_partial_observability(torch_cuda):
+    from metaworld_b200.vector_env import make_ml_envs
+    env = make_ml_envs("reach-v3", seed=3, meta_batch_size=4, split="train")
+    obs, _ = env.reset()
+    assert obs.shape == (4, 39) and obs.dtype == np.float64 and np.all(obs[:, 36:] == 0)   # test_new_api.py:146
+    assert all(env.get_attr("_partially_observable"))
+    t0 = [tuple(v) for v in env.get_attr("_last_rand_vec")]
+    env.call("sample_tasks")
+    t1 = [tuple(v) for v in env.get_attr("_last_rand_vec")]
+    assert t0 != t1
+    env.close()
+
+
+def test_full_size_properties(torch_cuda):
+    """4096 envs (BASELINE config 2): bounds, frame-stack identity, determinism of the whole batch, device sampler."""
+    torch = torch_cuda
+    from metaworld_b200.vector_env import make_mt_envs
+    finals = []
+    for rep in range(2):
+        env = make_mt_envs("reach-v3", seed=42, num_envs=4096, max_episode_steps=20)
+        env.reset()
+        env.enable_device_sampler()
+        g = torch.Generator(device=env.device); g.manual_seed(0)
+        prev = env.d_obs.clone()
+        for t in range(45):
+            a = torch.rand(4096, 4, device=env.device, generator=g) * 2 - 1
+            obs, rew, term, trunc, info = env.step_torch(a)
+            assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+            done = (term | trunc).bool()
+            assert torch.equal(obs[~done][:, 18:36], prev[~done][:, :18])
+            assert torch.equal(obs[done][:, 18:36], obs[done][:, :18])
+            assert bool(done.all()) == (t % 20 == 19)
+            prev = obs.clone()
+        o = obs.cpu().numpy()
+        assert (o[:, 0] >= -0.525).all() and (o[:, 0] <= 0.525).all() and (o[:, 2] >= -0.0525).all() and (o[:, 2] <= 0.7).all()
+        assert (o[:, 3] >= 0).all() and (o[:, 3] <= 1).all() and (rew.cpu().numpy() >= 0).all() and (rew.cpu().numpy() <= 10).all()
+        assert (o[:, 36:39] >= [-0.1, 0.8, 0.05]).all() and (o[:, 36:39] <= [0.1, 0.9, 0.3]).all()
+        finals.append(o)
+        c = env.engine.counters()
+        assert c["contacts_dropped"] == 0
+        env.close()
+    assert np.array_equal(finals[0], finals[1])

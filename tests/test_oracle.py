@@ -1,0 +1,177 @@
+"""CPU suite: the oracle (oracle/) against the reference's own importable pieces (committed golden vectors)
+and against analytic invariants of the physics it restates.  No GPU."""
+import copy
+import json
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return json.load(open(os.path.join(GOLD, "reward_utils.json")))
+
+
+def test_tolerance_matches_reference(gold):
+    from oracle.sawyer_env import tolerance
+    for x, lo, hi, m, sig, want in gold["tolerance"]:
+        assert tolerance(x, (lo, hi), m, sig) == pytest.approx(want, rel=1e-12, abs=1e-15)
+
+
+def test_hamacher_and_prism_match_reference(gold):
+    from oracle.sawyer_env import hamacher_product, rect_prism_tolerance
+    for a, b, want in gold["hamacher"]:
+        assert hamacher_product(a, b) == pytest.approx(want, rel=1e-12, abs=1e-15)
+    for c, z, o, want in gold["rect_prism"]:
+        assert rect_prism_tolerance(np.array(c), np.array(z), np.array(o)) == pytest.approx(want, rel=1e-12)
+    with pytest.raises(ValueError):
+        hamacher_product(1.2, 0.5)
+
+
+def test_quaternion_convention(gold):
+    from oracle.sawyer_env import mat2quat_xyzw
+    for R, q in gold["quat"]:
+        assert np.allclose(mat2quat_xyzw(R), q, atol=1e-12)
+
+
+def _free_model(dt):
+    from metaworld_b200 import modelzoo
+    m = copy.deepcopy(modelzoo.full_model("sawyer_reach_v3"))
+    a = m.arrays
+    a["dof_damping"][:] = 0
+    a["geom_contype"][:] = 0
+    a["geom_conaffinity"][:] = 0
+    for k in ("eq_obj1id", "eq_obj2id", "eq_data", "eq_solref", "eq_solimp"):
+        a[k] = a[k][:0]
+    a["jnt_limited"][:] = 0
+    a["actuator_kp"][:] = 0
+    a["dof_armature"][:] = 0.001
+    a["body_inertia"][m.names["body"].index("obj")] = [0.001, 0.002, 0.0005]
+    m.opt["timestep"] = dt
+    return m
+
+
+def _energy_drift(dt, T=0.05):
+    from oracle import mjphys as P
+    m = _free_model(dt)
+    a = m.arrays
+    om = P.OModel(m)
+    d = P.OData(om)
+
+    def energy():
+        P.mj_forward(om, d)
+        M = d.qM.reshape(om.nv, om.nv)
+        v = d.qvel
+        return 0.5 * v @ M @ v + sum(a["body_mass"][b] * 9.81 * d.xipos.reshape(-1, 3)[b, 2] for b in range(om.nbody))
+
+    rng = np.random.default_rng(0)
+    d.qpos[:7] = rng.uniform(-1, 1, 7)
+    d.qpos[1] = -1.5
+    d.qvel[:] = rng.uniform(-1, 1, om.nv)
+    d.qvel[9:12] = [0.3, 0.2, 1]
+    d.qvel[12:15] = [3, -2, 1]
+    e0 = energy()
+    P.mj_step(om, d, int(round(T / dt)))
+    return energy() - e0
+
+
+def test_dynamics_energy_consistency():
+    """Frictionless, undamped, unconstrained arm + tumbling free body: the energy error of the semi-implicit
+    integrator must vanish linearly with dt (checks mass matrix, bias forces and free-joint integration together)."""
+    d1, d2 = _energy_drift(2e-4), _energy_drift(1e-4)
+    assert abs(d1) < 5e-3
+    assert d1 / d2 == pytest.approx(2.0, rel=0.05)
+
+
+def test_weld_tracks_mocap_and_object_rests():
+    from oracle.tasks import TASKS
+    env = TASKS["reach-v3"]()
+    env.set_task_vec([0.05, 0.65, 0.02, -0.05, 0.85, 0.2], False)
+    obs, _ = env.reset()
+    assert np.allclose(obs[:3], [0, 0.6, 0.2], atol=5e-3)          # hand reached hand_init_pos
+    assert np.allclose(obs[4:7], [0.05, 0.65, 0.02], atol=1e-9)    # object placed by _set_obj_xyz
+    assert obs[36:39] == pytest.approx([-0.05, 0.85, 0.2])
+    for _ in range(20):
+        obs, r, term, trunc, info = env.step(np.zeros(4, np.float32))
+    assert abs(obs[6] - 0.0194) < 1e-3                              # cylinder rests on the table (half height 0.02)
+    f = [env.data.efc_force[c.efc_address] for c in env.data.contact if c.efc_address >= 0]
+    assert len(f) >= 1 and abs(sum(f) - 0.75 * 9.81) < 1.5          # normal force ~ weight (rocking single contact)
+    assert set(info) == {"success", "near_object", "grasp_success", "grasp_reward", "in_place_reward", "obj_to_target", "unscaled_reward"}
+
+
+def test_reach_p_controller_succeeds():
+    from oracle.tasks import TASKS
+    env = TASKS["reach-v3"]()
+    env.set_task_vec([0.0, 0.6, 0.02, 0.08, 0.88, 0.25], False)
+    obs, _ = env.reset()
+    ok = 0
+    for _ in range(150):
+        a = np.zeros(4, np.float32)
+        a[:3] = np.clip((env._target_pos - obs[:3]) * 10, -1, 1)
+        obs, r, term, trunc, info = env.step(a)
+        ok = max(ok, info["success"])
+    assert ok == 1.0 and r == pytest.approx(10.0)
+
+
+def test_obs_layout_identities():
+    """tests/helpers.py:4-33 of the reference: layout identities of the 39-vector."""
+    from oracle.tasks import TASKS
+    env = TASKS["reach-v3"]()
+    env.set_task_vec([0.02, 0.62, 0.02, -0.08, 0.82, 0.1], False)
+    prev, _ = env.reset()
+    rng = np.random.default_rng(3)
+    for _ in range(5):
+        obs, *_ = env.step(rng.uniform(-1, 1, 4).astype(np.float32))
+        assert np.all(obs[-3:] == env._target_pos)
+        assert np.all(obs[:3] == env.get_endeff_pos())
+        assert np.all(obs[4:7] == env._get_pos_objects()[:3])
+        assert np.all(obs[18:36] == prev[:18])
+        prev = obs
+    with pytest.raises(ValueError):
+        env.curr_path_length = 500
+        env.step(np.zeros(4, np.float32))
+
+
+def test_narrowphase_analytic_cases():
+    """box-box / sphere-box / capsule-box / cylinder-box (GJK+EPA) against hand-computed configurations."""
+    from metaworld_b200 import mjcf
+    from oracle import mjphys as P
+    import tempfile, textwrap
+    xml = textwrap.dedent("""
+    <mujoco><compiler angle="radian"/><option timestep="0.0025" cone="elliptic"/>
+      <worldbody>
+        <geom name="table" type="box" size="1 1 0.1" pos="0 0 -0.1" contype="0" conaffinity="1"/>
+        <body name="b" pos="0 0 0.049"><freejoint/><geom name="bg" type="box" size="0.05 0.05 0.05" mass="1"/></body>
+        <body name="s" pos="0.5 0 0.029"><freejoint/><geom name="sg" type="sphere" size="0.03" mass="1"/></body>
+        <body name="c" pos="-0.5 0 0.019"><freejoint/><geom name="cg" type="capsule" size="0.02 0.1" euler="0 1.5707963267948966 0" mass="1"/></body>
+        <body name="y" pos="0 0.5 0.039"><freejoint/><geom name="yg" type="cylinder" size="0.03 0.04" mass="1"/></body>
+        <body mocap="true" name="mocap"/>
+      </worldbody>
+      <actuator><position joint="dummy1"/><position joint="dummy2"/></actuator>
+    </mujoco>""")
+    xml = xml.replace('<actuator><position joint="dummy1"/><position joint="dummy2"/></actuator>', "")
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "m.xml")
+        open(p, "w").write(xml)
+        m = mjcf.load(p)
+    om = P.OModel(m)
+    d = P.OData(om)
+    P.mj_forward(om, d)
+    cons = d.contact
+    by = {}
+    for c in cons:
+        by.setdefault((m.names["geom"][c.geom1], m.names["geom"][c.geom2]), []).append(c)
+    box = by[("table", "bg")]
+    assert len(box) == 4 and all(abs(c.dist + 0.001) < 1e-9 for c in box)
+    assert all(abs(abs(c.pos[0]) - 0.05) < 1e-9 and abs(abs(c.pos[1]) - 0.05) < 1e-9 for c in box)
+    sph = by[("sg", "table")]
+    assert len(sph) == 1 and abs(sph[0].dist + 0.001) < 1e-9 and abs(sph[0].frame[2] + 1) < 1e-9
+    cap = by[("cg", "table")]
+    assert len(cap) == 2 and all(abs(c.dist + 0.001) < 1e-9 for c in cap)
+    assert sorted(round(c.pos[0], 6) for c in cap) == [-0.6, -0.4]
+    cyl = by[("yg", "table")]
+    assert len(cyl) == 1 and abs(cyl[0].dist + 0.001) < 1e-7 and abs(cyl[0].frame[2] + 1) < 1e-6
+    assert abs(cyl[0].pos[0]) < 1e-6 and abs(cyl[0].pos[1] - 0.5) < 1e-6       # under the cylinder axis
