@@ -20,6 +20,12 @@ def write_header():
     if not os.path.exists(path) or open(path).read() != txt:
         with open(path, "w") as f:
             f.write(txt)
+    from . import tasks
+    p2 = os.path.join(CSRC, "mw_task_ids.h")
+    txt2 = tasks.emit_task_enum()
+    if not os.path.exists(p2) or open(p2).read() != txt2:
+        with open(p2, "w") as f:
+            f.write(txt2)
     return path
 
 
@@ -27,7 +33,7 @@ def needs_build():
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS + ["mw_model.h"]] + [os.path.join(_HERE, "lower.py"),
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS + ["mw_model.h", "mw_task_ids.h"]] + [os.path.join(_HERE, "lower.py"), os.path.join(_HERE, "tasks.py"),
             os.path.join(_HERE, "..", "include", "metaworld_b200.h")]
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 

@@ -34,7 +34,7 @@ static_assert(sizeof(MwSnapshot) == 192 * 4, "MwSnapshot must be 192 floats");
 // per-task constants that are not part of the physics model (host fills from metaworld_b200/tasks.py)
 struct MwTaskConst {
   int task_id, nframe_task, main_geom, pad;
-  float hand_init[3], mocap_lo[3], mocap_hi[3], goal_lo[3], goal_hi[3];
+  float hand_init[3], mocap_lo[3], mocap_hi[3], goal_lo[3], goal_hi[3], movable_pos0[3];
   float p[16];
 };
 

@@ -20,7 +20,7 @@ SO_PATH = os.path.join(_HERE, "libmwb200.so")
 
 TASKCONST_DTYPE = np.dtype([("task_id", "i4"), ("nframe_task", "i4"), ("main_geom", "i4"), ("pad", "i4"),
                             ("hand_init", "f4", 3), ("mocap_lo", "f4", 3), ("mocap_hi", "f4", 3),
-                            ("goal_lo", "f4", 3), ("goal_hi", "f4", 3), ("p", "f4", 16)])
+                            ("goal_lo", "f4", 3), ("goal_hi", "f4", 3), ("movable_pos0", "f4", 3), ("p", "f4", 16)])
 ENVSTATE_DTYPE = np.dtype([("qpos", "f4", 18), ("qvel", "f4", 17), ("warm", "f4", 17), ("mocap_pos", "f4", 3),
                            ("prev_obs", "f4", 18), ("shift", "f4", 3), ("target", "f4", 3), ("obj_init", "f4", 3),
                            ("init_tcp", "f4", 3), ("scal", "f4", 16), ("path_len", "f4"),
@@ -90,6 +90,9 @@ def task_const(spec: TaskSpec, lw: lower.Lowered) -> np.ndarray:
     tc["hand_init"] = spec.hand_init_pos
     tc["mocap_lo"], tc["mocap_hi"] = spec.hand_low, spec.hand_high
     tc["goal_lo"], tc["goal_hi"] = spec.goal_low, spec.goal_high
+    if spec.movable:
+        m = modelzoo.full_model(spec.xml)
+        tc["movable_pos0"] = m.arrays["body_pos"][m.names["body"].index(spec.movable)]
     p = np.zeros(16, dtype=np.float32)
     p[: len(spec.params)] = spec.params
     # collider slots of the two finger pads (touching_object, sawyer_xyz_env.py:401-440)

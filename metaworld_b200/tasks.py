@@ -48,12 +48,59 @@ def _cat(a, b):
     return tuple(a) + tuple(b)
 
 
+_HL, _HH = (-0.5, 0.40, 0.05), (0.5, 1, 0.5)        # hand_low / hand_high shared by every V3 task
+_H0 = (0.0, 0.6, 0.2)
+
 _SPECS = [
-    # ---- metaworld/envs/sawyer_reach_v3.py:40-75,125-129
-    TaskSpec("reach-v3", 0, "sawyer_reach_v3", None, _OBJ, (0.0, 0.6, 0.2), (-0.5, 0.40, 0.05), (0.5, 1, 0.5),
+    # ---- reach / push / pick-place family (sawyer_reach_v3.py, sawyer_push_v3.py, sawyer_pick_place_v3.py)
+    TaskSpec("reach-v3", 0, "sawyer_reach_v3", None, _OBJ, _H0, _HL, _HH,
              _cat((-0.1, 0.6, 0.02), (-0.1, 0.8, 0.05)), _cat((0.1, 0.7, 0.02), (0.1, 0.9, 0.3)),
              (-0.1, 0.8, 0.05), (0.1, 0.9, 0.3), reject=(_XY[0], _XY[1], 0.15)),
+    TaskSpec("push-v3", 1, "sawyer_push_v3", None, _OBJ, _H0, _HL, _HH,
+             _cat((-0.1, 0.6, 0.02), (-0.1, 0.8, 0.01)), _cat((0.1, 0.7, 0.02), (0.1, 0.9, 0.02)),
+             (-0.1, 0.8, 0.01), (0.1, 0.9, 0.02), reject=(_XY[0], _XY[1], 0.15)),
+    TaskSpec("pick-place-v3", 2, "sawyer_pick_place_v3", None, _OBJ, _H0, _HL, _HH,
+             _cat((-0.1, 0.6, 0.02), (-0.1, 0.8, 0.05)), _cat((0.1, 0.7, 0.02), (0.1, 0.9, 0.3)),
+             (-0.1, 0.8, 0.05), (0.1, 0.9, 0.3), reject=(_XY[0], _XY[1], 0.15)),
+    # ---- sawyer_door_v3.py (door-open)
+    TaskSpec("door-open-v3", 3, "sawyer_door_pull", "door", [("geom", "handle")], _H0, _HL, _HH,
+             (0.0, 0.85, 0.15), (0.1, 0.95, 0.15), (-0.3, 0.4, 0.1499), (-0.2, 0.5, 0.1501), main_geom=None),
+    # ---- sawyer_drawer_open_v3.py / sawyer_drawer_close_v3.py  (goal_space = hand box)
+    TaskSpec("drawer-open-v3", 4, "sawyer_drawer", "drawer", [("body", "drawer_link")], _H0, _HL, _HH,
+             (-0.1, 0.9, 0.0), (0.1, 0.9, 0.0), _HL, _HH),
+    TaskSpec("drawer-close-v3", 5, "sawyer_drawer", "drawer", [("body", "drawer_link")], _H0, _HL, _HH,
+             (-0.1, 0.9, 0.0), (0.1, 0.9, 0.0), _HL, _HH),
+    # ---- sawyer_button_press_topdown_v3.py
+    TaskSpec("button-press-topdown-v3", 6, "sawyer_button_press_topdown", "box",
+             [("body", "button"), ("site", "hole"), ("site", "buttonStart")], (0, 0.4, 0.2), _HL, _HH,
+             (-0.1, 0.8, 0.115), (0.1, 0.9, 0.115), _HL, _HH, main_geom="btnGeom"),
+    # ---- sawyer_peg_insertion_side_v3.py
+    TaskSpec("peg-insert-side-v3", 7, "sawyer_peg_insertion_side", "box",
+             [("site", "pegGrasp"), ("site", "pegHead"), ("body", "peg"),
+              ("site", "bottom_right_corner_collision_box_1"), ("site", "top_left_corner_collision_box_1"),
+              ("site", "bottom_right_corner_collision_box_2"), ("site", "top_left_corner_collision_box_2")],
+             _H0, _HL, _HH, _cat((0.0, 0.5, 0.02), (-0.35, 0.4, -0.001)), _cat((0.2, 0.7, 0.02), (-0.25, 0.7, 0.001)),
+             (-0.32, 0.4, 0.129), (-0.22, 0.7, 0.131), reject=(_XY[0], _XY[1], 0.1), main_geom=None),
+    # ---- sawyer_window_open_v3.py / sawyer_window_close_v3.py
+    TaskSpec("window-open-v3", 8, "sawyer_window_horizontal", "window", [("site", "handleOpenStart")], (0, 0.4, 0.2), _HL, _HH,
+             (-0.1, 0.7, 0.16), (0.1, 0.9, 0.16), _HL, _HH, main_geom=None),
+    TaskSpec("window-close-v3", 9, "sawyer_window_horizontal", "window", [("site", "handleCloseStart")], (0, 0.4, 0.2), _HL, _HH,
+             (0.0, 0.75, 0.2), (0.0, 0.9, 0.2), _HL, _HH, main_geom=None),
 ]
 
 TASKS = {t.name: t for t in _SPECS}
 TASK_IDS = {t.name: t.task_id for t in _SPECS}
+assert sorted(TASK_IDS.values()) == list(range(len(_SPECS)))
+
+
+def enum_name(name: str) -> str:
+    return "T_" + name[:-3].upper().replace("-", "_")
+
+
+def emit_task_enum() -> str:
+    """C enum of task ids for csrc/mw_tasks_gen.cuh (written by build.write_header)."""
+    lines = ["/* GENERATED by metaworld_b200/tasks.py:emit_task_enum -- do not edit. */", "#pragma once", "enum {"]
+    for t in sorted(_SPECS, key=lambda t: t.task_id):
+        lines.append(f"  {enum_name(t.name)} = {t.task_id},")
+    lines += ["  T_NTASK", "};"]
+    return "\n".join(lines) + "\n"
