@@ -78,6 +78,11 @@ int mw_get_state(mw_engine*, void* out_host);
 int mw_set_state(mw_engine*, const void* in_host);
 /* debug: run nstep raw physics substeps (mj_step) on every env with fixed ctrl, no reward/obs */
 int mw_debug_substeps(mw_engine*, int nstep, const float* ctrl2 /*host [2]*/, void* stream);
+/* debug: one forward pass (mj_forward) per env, no state change; dumps per env mw_debug_dump_floats() floats:
+ * contacts [MAXCON][12] = dist, pos[3], normal[3], geom1, geom2 (source geom ids), normal force, dim, efc row;
+ * then qacc[MAXDOF]; then ncon, nefc, solver iterations.  dump: DEV float [n_envs * mw_debug_dump_floats()] */
+int mw_debug_forward(mw_engine*, const float* ctrl2 /*host [2]*/, float* dump, void* stream);
+int mw_debug_dump_floats(void);
 /* counters accumulated since the last call: [0] kernel launches, [1] env steps, [2] contacts dropped,
  * [3] solver iterations (sum over forward passes), [4] forward passes */
 int mw_get_counters(mw_engine*, unsigned long long* out5);

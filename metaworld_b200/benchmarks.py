@@ -67,8 +67,12 @@ def draw_rand_vec(spec, rs: np.random.RandomState):
     lo, hi = spec.rand_low, spec.rand_high
     v = rs.uniform(lo, hi, size=lo.size).astype(np.float64)
     if spec.reject is not None:
-        (a0, a1), (b0, b1), thr = spec.reject
-        while np.linalg.norm(v[a0:a1] - v[b0:b1]) < thr:
+        (a0, a1), other, thr = spec.reject
+
+        def ref(v):   # either another slice of the vector or a fixed point (sweep-into: the constant goal)
+            return v[other[0]:other[1]] if isinstance(other[0], int) else np.asarray(other)
+
+        while np.linalg.norm(v[a0:a1] - ref(v)) < thr:
             v = rs.uniform(lo, hi, size=lo.size).astype(np.float64)
     return v
 

@@ -8,6 +8,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 SO = os.path.join(_HERE, "libmwb200.so")
+SO_F64 = os.path.join(_HERE, "libmwb200_f64.so")   # same kernels with real=double (parity-analysis build)
 SOURCES = ["mw_engine.cu"]
 HEADERS = ["mw_math.cuh", "mw_collide.cuh", "mw_physics.cuh", "mw_tasks.cuh", "mw_tasks_gen.cuh"]
 
@@ -40,6 +41,8 @@ def needs_build():
 
 def build(force=False, verbose=False, real_double=False, extra=()):
     write_header()
+    if real_double:
+        return _build_f64(force, verbose)
     if not force and not needs_build():
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -57,6 +60,24 @@ def build(force=False, verbose=False, real_double=False, extra=()):
     if verbose:
         print(r.stdout + r.stderr)
     return SO
+
+
+def _build_f64(force=False, verbose=False):
+    if not force and os.path.exists(SO_F64) and os.path.getmtime(SO_F64) >= max(
+            os.path.getmtime(os.path.join(CSRC, f)) for f in SOURCES + HEADERS):
+        return SO_F64
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-DMW_REAL_DOUBLE", "-DWARPS_PER_BLOCK=3", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+           "-Xcompiler", "-fPIC", "-shared", "-o", SO_F64] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        cmd[1:1] = ["-Xptxas", "-v"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed (f64 build)")
+    if verbose:
+        print(r.stdout + r.stderr)
+    return SO_F64
 
 
 if __name__ == "__main__":

@@ -451,9 +451,9 @@ DEV void simplex_weights(const SV* s, int n, real* w) {
   } else if (n == 3) closest_tri(s[0].v, s[1].v, s[2].v, w);
 }
 
-#define EPA_MAXV 40
-#define EPA_MAXF 80
-#define EPA_MAXE 64
+#define EPA_MAXV 80
+#define EPA_MAXF 160
+#define EPA_MAXE 96
 struct EFace { int v[3]; real n[3], d; int alive; };
 struct EpaWs { SV V[EPA_MAXV]; EFace F[EPA_MAXF]; int edge[EPA_MAXE][2]; };
 #define EPA_WS_WORDS ((int)(sizeof(EpaWs) / 4))
@@ -473,28 +473,74 @@ DEV bool epa_add_face(EpaWs* W, int* nf, int a, int b, int c) {
 }
 
 
-// Face-on contact of a cylinder cap with a box face: every point of the overlap patch is a valid EPA witness, so the
-// contact point is implementation-defined.  We take the pressure centroid of the (linearly penetrating) cap: offset
-// r^2 sin(tilt) / (4 p0) from the cap centre towards the deepest rim point (p0 = penetration of the cap centre),
-// clamped to the rim.  Every other configuration is left untouched.
-DEV void refine_cyl_box(const DShape& A, const DShape& B, RawCon* o) {
+// Face-on contact between a cylinder and a box face (cap-on-face or generator-line-on-face): every point of the
+// contact patch is a valid EPA witness, so the contact *point* is implementation-defined in the reference physics.
+// We take the pressure centroid of the patch under a linear penetration profile, clipped to the overlap with the
+// box face (continuous in the pose; removes rim-to-rim chatter of resting cylinders).  Other configurations are
+// left as EPA/GJK produced them.
+__device__ __noinline__ void refine_cyl_box(const DShape& A, const DShape& B, RawCon* o) {
   if (A.type != G_CYLINDER || B.type != G_BOX) return;
-  real nl[3], nb[3]; mat_tmulvec(nl, A.mat, o->normal); mat_tmulvec(nb, B.mat, o->normal);
-  if (fabs(nl[2]) < (real)0.9) return;
-  int k = 0; for (int i = 1; i < 3; i++) if (fabs(nb[i]) > fabs(nb[k])) k = i;
-  if (fabs(nb[k]) < (real)0.99999) return;
-  real r = A.size[0], depth = -o->dist, rad = sqrt(nl[0] * nl[0] + nl[1] * nl[1]);
-  real p0 = depth - r * rad;
-  if (p0 <= 0) return;
-  real sbar = rad > (real)1e-12 ? fmin(r, r * r * rad / (4 * p0)) : (real)0;
-  real pl[3] = {0, 0, nl[2] > 0 ? A.size[1] : -A.size[1]}, pw[3], t[3], pb[3];
-  if (rad > (real)1e-12) { pl[0] = nl[0] / rad * sbar; pl[1] = nl[1] / rad * sbar; }
-  mat_mulvec(pw, A.mat, pl); v3add(pw, pw, A.pos);
-  v3sub(t, pw, B.pos); mat_tmulvec(pb, B.mat, t);
-  for (int i = 0; i < 3; i++) if (i != k && fabs(pb[i]) > B.size[i]) return;
-  real pen = p0 + sbar * rad;
+  real nb[3]; mat_tmulvec(nb, B.mat, o->normal);
+  int k = 0; for (int q = 1; q < 3; q++) if (fabs(nb[q]) > fabs(nb[k])) k = q;
+  if (fabs(nb[k]) < (real)0.99999) return;                       /* the contact normal must be a face normal of the box */
+  const real sgn = nb[k] > 0 ? (real)1 : (real)-1;
+  const int i = (k + 1) % 3, j = (k + 2) % 3;
+  const real r = A.size[0], h = A.size[1];
+  real ax[3], a[3], t[3], cB[3];
+  mat_col(ax, A.mat, 2); mat_tmulvec(a, B.mat, ax);
+  v3sub(t, A.pos, B.pos); mat_tmulvec(cB, B.mat, t);
+  const real ak = a[k] * sgn;
+  real P[3], pen;
+  if (fabs(ak) > (real)0.9) {
+    /* ---- cap on face */
+    const real cs = ak > 0 ? (real)1 : (real)-1;
+    real C[3], acap[3], g[3];
+    for (int q = 0; q < 3; q++) { acap[q] = cs * a[q]; C[q] = cB[q] + cs * h * a[q]; }
+    const real pen0 = sgn * C[k] + B.size[k];
+    for (int q = 0; q < 3; q++) g[q] = -(sgn * acap[k]) * acap[q];
+    g[k] += sgn;
+    const real st = v3norm(g);                                   /* sin(tilt) */
+    real sbar = 0;
+    if (st > (real)1e-9) sbar = pen0 > 0 ? fmin(r, r * r * st / (4 * pen0)) : r;
+    for (int q = 0; q < 3; q++) P[q] = C[q] + (st > (real)1e-9 ? g[q] / st * sbar : (real)0);
+    const int axs[2] = {i, j};
+    for (int q = 0; q < 2; q++) {
+      const int u = axs[q];
+      const real lo = fmax(C[u] - r, -B.size[u]), hi = fmin(C[u] + r, B.size[u]);
+      if (lo > hi) return;
+      P[u] = fmin(fmax(P[u], lo), hi);
+    }
+    P[k] = C[k] - (acap[i] * (P[i] - C[i]) + acap[j] * (P[j] - C[j])) / acap[k];
+    pen = sgn * P[k] + B.size[k];
+  } else if (fabs(ak) < (real)0.1) {
+    /* ---- generator line on face */
+    real d[3], L0[3];
+    for (int q = 0; q < 3; q++) d[q] = -(sgn * a[k]) * a[q];
+    d[k] += sgn;
+    v3normalize(d);
+    for (int q = 0; q < 3; q++) L0[q] = cB[q] + r * d[q];
+    real t0 = -h, t1 = h;
+    const int axs[2] = {i, j};
+    for (int q = 0; q < 2; q++) {
+      const int u = axs[q];
+      if (fabs(a[u]) > (real)1e-9) {
+        const real ta = (-B.size[u] - L0[u]) / a[u], tb = (B.size[u] - L0[u]) / a[u];
+        t0 = fmax(t0, fmin(ta, tb)); t1 = fmin(t1, fmax(ta, tb));
+      } else if (fabs(L0[u]) > B.size[u]) return;
+    }
+    if (t0 > t1) return;
+    const real tm = (real)0.5 * (t0 + t1), Lh = (real)0.5 * (t1 - t0), sl = sgn * a[k];
+    const real penm = sgn * (L0[k] + tm * a[k]) + B.size[k];
+    real off;
+    if (penm > 0) off = fmin(fmax(sl * Lh * Lh / (3 * penm), -Lh), Lh);
+    else off = sl > 0 ? Lh : (sl < 0 ? -Lh : (real)0);
+    const real ts = tm + off;
+    for (int q = 0; q < 3; q++) P[q] = L0[q] + ts * a[q];
+    pen = sgn * P[k] + B.size[k];
+  } else return;
   o->dist = -pen;
-  v3addscl(o->pos, pw, o->normal, (real)-0.5 * pen);
+  P[k] -= sgn * (real)0.5 * pen;
+  mat_mulvec(o->pos, B.mat, P); v3add(o->pos, o->pos, B.pos);
 }
 
 // Whole warp calls this with identical A, B.  The result (count 0/1, contact in *o) is valid on every lane.
@@ -514,7 +560,7 @@ __device__ __noinline__ int convex_pair(const DShape& A, const DShape& B, real m
       else {
         real vv = v3dot(v, v), vw = v3dot(v, w.v);
         if (vv - vw <= reltol * vv) status = 1;
-        else if (vw > 0 && vw / sqrt(vv) - ra - rb > margin) status = 3;
+        else if (vw > 0 && vw / sqrt(vv) - ra - rb > margin + (real)1e-4) status = 3;
         else {
           bool dup = false;
           for (int i = 0; i < n; i++) { real t[3]; v3sub(t, s[i].v, w.v); if (v3dot(t, t) < (real)1e-20) dup = true; }
@@ -540,10 +586,11 @@ __device__ __noinline__ int convex_pair(const DShape& A, const DShape& B, real m
     real dcore = v3norm(dvec);
     if (dcore > (real)1e-7) {
       real dist = dcore - ra - rb;
-      if (dist <= margin) {
+      if (dist <= margin + (real)1e-4) {      // slack: the analytic refinement below makes the final call
         v3scl(rc.normal, dvec, 1 / dcore); rc.dist = dist;
         for (int k = 0; k < 3; k++) rc.pos[k] = (real)0.5 * (wa[k] + rc.normal[k] * ra + wb[k] - rc.normal[k] * rb);
-        result = 1;
+        refine_cyl_box(A, B, &rc);
+        result = rc.dist <= margin ? 1 : -1;
       } else result = -1;
     } else status = 2;   // touching: let EPA resolve the direction
     if (result == -1) { result = 0; status = 3; }
@@ -553,7 +600,7 @@ __device__ __noinline__ int convex_pair(const DShape& A, const DShape& B, real m
     // ---- EPA.  phase 0: grow the simplex to a tetrahedron; phase 1: expand the polytope
     int nv = 0, nf = 0, k = 0, phase = 0, done = 0, bestf = -1;   // leader state
     real dirl[3] = {1, 0, 0};
-    for (int it = 0; it < 96; it++) {
+    for (int it = 0; it < 176; it++) {
       if (lane == 0) {
         // choose the next query direction
         if (phase == 0) {
@@ -637,7 +684,7 @@ __device__ __noinline__ int convex_pair(const DShape& A, const DShape& B, real m
         rc.dist = dist; v3copy(rc.normal, f->n);
         for (int q = 0; q < 3; q++) rc.pos[q] = (real)0.5 * (wa[q] + rc.normal[q] * ra + wb[q] - rc.normal[q] * rb);
         refine_cyl_box(A, B, &rc);
-        result = 1;
+        result = rc.dist <= margin ? 1 : 0;
       }
     }
   }

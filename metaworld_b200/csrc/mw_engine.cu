@@ -16,7 +16,9 @@
 #include "../../include/metaworld_b200.h"
 #include "mw_tasks.cuh"
 
-#define WARPS_PER_BLOCK 8
+#ifndef WARPS_PER_BLOCK
+#define WARPS_PER_BLOCK 6
+#endif
 #define BLOCK_THREADS (WARPS_PER_BLOCK * 32)
 
 static thread_local std::string g_err;
@@ -264,7 +266,7 @@ __global__ void k_reset(EngineDev e, int n, const int* __restrict__ env_ids, con
 
 __global__ void __launch_bounds__(BLOCK_THREADS, 1)
 k_substeps(EngineDev e, const int* __restrict__ block_model, const int* __restrict__ block_start, const int* __restrict__ block_count,
-           const int* __restrict__ perm, int nstep, float c0, float c1) {
+           const int* __restrict__ perm, int nstep, float c0, float c1, float* __restrict__ dump) {
   extern __shared__ __align__(16) unsigned char smem[];
   BlockShared* bs = (BlockShared*)smem;
   WarpShared* wsa = (WarpShared*)(smem + sizeof(BlockShared));
@@ -279,6 +281,21 @@ k_substeps(EngineDev e, const int* __restrict__ block_model, const int* __restri
   if (lane == 0) { ws->w.ctrl[0] = c0; ws->w.ctrl[1] = c1; }
   SYNCW();
   for (int s = 0; s < nstep; s++) { mw_forward(m, e.meshverts[mi], &ws->w, lane); mw_euler(m, &ws->w, lane); }
+  if (dump) {   // debug: one forward pass, then dump contacts [env][MW_MAXCON][12] and qacc [env][MW_MAXDOF] after them
+    mw_forward(m, e.meshverts[mi], &ws->w, lane);
+    float* d = dump + (size_t)env * (MW_MAXCON * 12 + MW_MAXDOF + 4);
+    for (int c = lane; c < MW_MAXCON; c += 32) {
+      const Contact* k = &ws->w.con[c];
+      bool ok = c < ws->w.ncon;
+      d[12 * c + 0] = ok ? (float)k->dist : 0.f;
+      for (int i = 0; i < 3; i++) { d[12 * c + 1 + i] = ok ? (float)k->pos[i] : 0.f; d[12 * c + 4 + i] = ok ? (float)k->frame[i] : 0.f; }
+      d[12 * c + 7] = ok ? (float)m->geom_srcid[k->g1] : -1.f; d[12 * c + 8] = ok ? (float)m->geom_srcid[k->g2] : -1.f;
+      d[12 * c + 9] = ok ? (float)k->fn : 0.f; d[12 * c + 10] = ok ? (float)k->dim : 0.f; d[12 * c + 11] = ok ? (float)k->row : -1.f;
+    }
+    if (lane < MW_MAXDOF) d[MW_MAXCON * 12 + lane] = (float)ws->w.qacc[lane];
+    if (lane == 0) { d[MW_MAXCON * 12 + MW_MAXDOF] = (float)ws->w.ncon; d[MW_MAXCON * 12 + MW_MAXDOF + 1] = (float)ws->w.nefc; d[MW_MAXCON * 12 + MW_MAXDOF + 2] = (float)ws->w.solver_iter; }
+    return;
+  }
   store_env(ws, e.state + env, lane);
 }
 
@@ -474,11 +491,19 @@ int mw_set_state(mw_engine* E, const void* in) {
 int mw_debug_substeps(mw_engine* E, int nstep, const float* ctrl2, void* stream) {
   if (!E || !E->d_state || nstep < 0 || !ctrl2) return fail(MW_ERR_ARG, "mw_debug_substeps");
   CK(cudaSetDevice(E->device));
-  k_substeps<<<E->n_blocks, BLOCK_THREADS, smem_bytes(), (cudaStream_t)stream>>>(E->dev(), E->d_block_model, E->d_block_start, E->d_block_count, E->d_perm, nstep, ctrl2[0], ctrl2[1]);
+  k_substeps<<<E->n_blocks, BLOCK_THREADS, smem_bytes(), (cudaStream_t)stream>>>(E->dev(), E->d_block_model, E->d_block_start, E->d_block_count, E->d_perm, nstep, ctrl2[0], ctrl2[1], nullptr);
   CK(cudaGetLastError());
   E->launches++;
   return MW_OK;
 }
+int mw_debug_forward(mw_engine* E, const float* ctrl2, float* dump_dev, void* stream) {
+  if (!E || !E->d_state || !ctrl2 || !dump_dev) return fail(MW_ERR_ARG, "mw_debug_forward");
+  CK(cudaSetDevice(E->device));
+  k_substeps<<<E->n_blocks, BLOCK_THREADS, smem_bytes(), (cudaStream_t)stream>>>(E->dev(), E->d_block_model, E->d_block_start, E->d_block_count, E->d_perm, 0, ctrl2[0], ctrl2[1], dump_dev);
+  CK(cudaGetLastError());
+  return MW_OK;
+}
+int mw_debug_dump_floats(void) { return MW_MAXCON * 12 + MW_MAXDOF + 4; }
 int mw_get_counters(mw_engine* E, unsigned long long* out5) {
   if (!E || !out5) return fail(MW_ERR_ARG, "mw_get_counters");
   CK(cudaSetDevice(E->device));

@@ -14,7 +14,7 @@
 
 #define NVP 17               // row stride of the dense nv x nv / nefc x nv matrices (odd: conflict-free columns)
 #ifndef MW_MAXCON
-#define MW_MAXCON 24
+#define MW_MAXCON 48
 #endif
 #define MW_MAXSCALAR 24      // weld (6) + joint-limit rows
 #define MW_MAXEFC (MW_MAXSCALAR + 4 * MW_MAXCON)
@@ -523,8 +523,9 @@ __device__ __noinline__ void mw_make_constraints(const MwModel* __restrict__ m, 
     w->eD[r] = 1 / Rr;
     w->eAref[r] = -rp.B * vel - rp.K * rp.imp * ldist;
   }
-  if (lane < ncon && w->con[lane].row >= 0) {
-    Contact* con = &w->con[lane];
+  for (int ci = lane; ci < ncon; ci += 32) {
+    Contact* con = &w->con[ci];
+    if (con->row < 0) continue;
     int r0 = con->row, dim = con->dim;
     real tran = m->geom_invw[con->g1][0] + m->geom_invw[con->g2][0];
     real rot = m->geom_invw[con->g1][1] + m->geom_invw[con->g2][1];
@@ -599,8 +600,9 @@ DEV real mw_cone(const WarpScratch* w, const Contact* con, const real* x, real* 
 DEV real mw_constraint_eval(WarpScratch* w, int lane, bool want_hess) {
   real cost = 0;
   if (lane < w->nscalar) { real f, hd; cost += mw_scalar_row(w, lane, w->eJar[lane], &f, &hd); w->eF[lane] = f; w->eHd[lane] = hd; }
-  if (lane < w->ncon && w->con[lane].row >= 0) {
-    Contact* con = &w->con[lane];
+  for (int ci = lane; ci < w->ncon; ci += 32) {
+    Contact* con = &w->con[ci];
+    if (con->row < 0) continue;
     real x[4] = {0, 0, 0, 0}, f[4]; int zone;
     for (int k = 0; k < con->dim; k++) x[k] = w->eJar[con->row + k];
     cost += mw_cone(w, con, x, f, want_hess ? con->H : nullptr, &zone);
@@ -615,8 +617,9 @@ DEV void mw_linesearch_eval(const WarpScratch* w, int lane, real alpha, real* c,
     real jv = w->eJv[lane], x = w->eJar[lane] + alpha * jv, D = w->eD[lane];
     if (lane < w->nweld || x < 0) { cc += (real)0.5 * D * x * x; gg += D * x * jv; h2 += D * jv * jv; }
   }
-  if (lane < w->ncon && w->con[lane].row >= 0) {
-    const Contact* con = &w->con[lane];
+  for (int ci = lane; ci < w->ncon; ci += 32) {
+    const Contact* con = &w->con[ci];
+    if (con->row < 0) continue;
     const int r0 = con->row, dim = con->dim; const real mu = con->mu;
     real fr[4] = {0, con->fr1, con->fr1, con->fr3};
     real x0 = w->eJar[r0] + alpha * w->eJv[r0];

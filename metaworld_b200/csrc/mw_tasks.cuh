@@ -129,4 +129,21 @@ DEV real gripper_caging_reward(const TaskCtx& c, const real* obj_pos, real obj_r
   return cg;
 }
 
+// task-local caging override shared by push-back / sweep / sweep-into / soccer (e.g. sawyer_push_back_v3.py:160-254);
+// `init_left_pad` / `init_right_pad` alias the live pad positions in the reference (sawyer_xyz_env.py:236-237)
+DEV real grip_caging(const TaskCtx& c, const real* obj, real obj_radius, real grip_add, real xz_c) {
+  real lp[3], rp[3], tcp[3];
+  mw_frame_pos(c.m, c.w, F_LPAD, lp); mw_frame_pos(c.m, c.w, F_RPAD, rp); tcp_center(c, tcp);
+  real dl = lp[1] - obj[1], dr = obj[1] - rp[1];
+  real rm = fabs(fabs(obj[1] - rp[1]) - (real)0.05), lm = fabs(fabs(obj[1] - lp[1]) - (real)0.05);
+  real rc = tol_long_tail(dr, obj_radius, (real)0.05, rm), lc = tol_long_tail(dl, obj_radius, (real)0.05, lm);
+  real rg = tol_long_tail(dr, obj_radius, obj_radius + grip_add, rm), lg = tol_long_tail(dl, obj_radius, obj_radius + grip_add, lm);
+  real ycag = hamacher(rc, lc), ygrip = hamacher(rg, lg);
+  real ix = (real)c.s->obj_init[0] - (real)c.s->init_tcp[0], iz = (real)c.s->obj_init[2] - (real)c.s->init_tcp[2];
+  real ex = tcp[0] - obj[0], ez = tcp[2] - obj[2];
+  real xz = tol_long_tail(sqrt(ex * ex + ez * ez), 0, xz_c, sqrt(ix * ix + iz * iz) - xz_c);
+  real caging = hamacher(ycag, xz);
+  return (caging + (caging > (real)0.95 ? ygrip : (real)0)) / 2;
+}
+
 #include "mw_tasks_gen.cuh"

@@ -27,8 +27,14 @@ DEV void obs_body_geomquat(const TaskCtx& c, int fbody, int fgeom, real* o) {
 DEV void task_obs_objects(const TaskCtx& c, real* o) {
   for (int i = 0; i < 14; i++) o[i] = 0;
   switch (c.tc->task_id) {
-    case T_REACH: case T_PUSH: case T_PICK_PLACE:
+    case T_REACH: case T_PUSH: case T_PICK_PLACE: case T_REACH_WALL: case T_SWEEP_INTO:
       obs_body_geomquat(c, F_TASK0, F_TASK0 + 1, o);   // body "obj", geom "objGeom"  (sawyer_reach_v3.py:99-104)
+      break;
+    case T_PUSH_WALL: case T_PICK_PLACE_WALL: case T_PUSH_BACK:   // geom objGeom xpos + scipy quat (sawyer_push_wall_v3.py:120-126)
+      obs_body_geomquat(c, F_TASK0 + 1, F_TASK0 + 1, o);
+      break;
+    case T_SWEEP: case T_HAND_INSERT: case T_PICK_OUT_OF_HOLE:    // body obj xpos + xquat (sawyer_sweep_v3.py:92-97)
+      mw_frame_pos(c.m, c.w, F_TASK0, o); mw_frame_quat(c.m, c.w, F_TASK0, o + 3);
       break;
     case T_DOOR_OPEN: {                                // geom "handle" xpos + scipy quat (sawyer_door_v3.py:97-103)
       real R[9]; mw_frame_pos(c.m, c.w, F_TASK0, o); frame_mat(c.m, c.w, F_TASK0, R); mat2quat_scipy(R, o + 3);
@@ -65,6 +71,103 @@ DEV void task_reward(const TaskCtx& c, const real* obs, real* reward, real* info
       *reward = 10 * in_place;
       info[INFO_SUCCESS] = d <= (real)0.05; info[INFO_NEAR_OBJECT] = d; info[INFO_GRASP_SUCCESS] = 1;
       info[INFO_GRASP_REWARD] = d; info[INFO_IN_PLACE] = in_place; info[INFO_OBJ_TO_TARGET] = d; info[INFO_UNSCALED] = *reward;
+    } break;
+    case T_REACH_WALL: {   // sawyer_reach_wall_v3.py:84-101,145-167
+      real hand0[3] = {c.tc->hand_init[0], c.tc->hand_init[1], c.tc->hand_init[2]};
+      real d = dist3(tcp, target);
+      real in_place = tol_long_tail(d, 0, (real)0.05, dist3(hand0, target));
+      *reward = 10 * in_place;
+      info[INFO_SUCCESS] = d <= (real)0.05; info[INFO_IN_PLACE] = in_place; info[INFO_OBJ_TO_TARGET] = d; info[INFO_UNSCALED] = *reward;
+    } break;
+    case T_PUSH_WALL: case T_PICK_PLACE_WALL: {   // sawyer_push_wall_v3.py:89-118,173-236 ; sawyer_pick_place_wall_v3.py:85-115,177-252
+      bool pick = c.tc->task_id == T_PICK_PLACE_WALL;
+      const real* obj = obs + 4; real opened = obs[3];
+      real oi[3] = {c.s->obj_init[0], c.s->obj_init[1], c.s->obj_init[2]};
+      real mid[3] = {pick ? target[0] : (real)-0.05, (real)0.77, pick ? (real)0.25 : obj[2]};
+      real sc[3] = {pick ? (real)1 : (real)3, 1, pick ? (real)3 : (real)1};
+      real a[3], b[3];
+      for (int i = 0; i < 3; i++) { a[i] = (obj[i] - mid[i]) * sc[i]; b[i] = (oi[i] - mid[i]) * sc[i]; }
+      real tcp_to_obj = dist3(obj, tcp), o2t = dist3(obj, target);
+      real p1 = tol_long_tail(v3norm(a), 0, (real)0.05, v3norm(b));
+      real p2 = tol_long_tail(o2t, 0, (real)0.05, dist3(oi, target));
+      real g = gripper_caging_reward(c, obj, (real)0.015, (real)0.05, (real)0.01, (real)0.005, 1, pick ? 0 : 1);
+      real r;
+      if (!pick) {
+        r = 2 * g;
+        if (tcp_to_obj < (real)0.02 && opened > 0) { r = 2 * g + 1 + 4 * p1; if (obj[1] > (real)0.75) r = 2 * g + 1 + 4 + 3 * p2; }
+      } else {
+        real ipg = hamacher(g, p1);
+        r = ipg;
+        if (tcp_to_obj < (real)0.02 && opened > 0 && (obj[2] - (real)0.015 > oi[2])) { r = ipg + 1 + 4 * p1; if (obj[1] > (real)0.75) r = ipg + 1 + 4 + 3 * p2; }
+      }
+      if (o2t < (real)0.05) r = 10;
+      *reward = r;
+      bool touch = touching_object(c, c.tc->main_geom, (int)c.tc->p[14], (int)c.tc->p[15]);
+      info[INFO_SUCCESS] = o2t <= (real)0.07; info[INFO_NEAR_OBJECT] = tcp_to_obj <= (real)0.03;
+      info[INFO_GRASP_SUCCESS] = touch && opened > 0 && (obj[2] - (real)0.02 > oi[2]);
+      info[INFO_GRASP_REWARD] = g; info[INFO_IN_PLACE] = p2; info[INFO_OBJ_TO_TARGET] = o2t; info[INFO_UNSCALED] = r;
+    } break;
+    case T_PUSH_BACK: {   // sawyer_push_back_v3.py:69-98,256-294
+      const real* obj = obs + 4; real opened = obs[3];
+      real oi[3] = {c.s->obj_init[0], c.s->obj_init[1], c.s->obj_init[2]};
+      real tcp_to_obj = dist3(obj, tcp), t2o = dist3(obj, target), t2oi = dist3(oi, target);
+      real in_place = tol_long_tail(t2o, 0, (real)0.05, t2oi);
+      real g = grip_caging(c, obj, (real)0.007, (real)0.003, (real)0.01);
+      real r = hamacher(g, in_place);
+      if (tcp_to_obj < (real)0.01 && opened > 0 && opened < (real)0.55 && (t2oi - t2o > (real)0.01)) r += 1 + 5 * in_place;
+      if (t2o < (real)0.05) r = 10;
+      *reward = r;
+      bool touch = touching_object(c, c.tc->main_geom, (int)c.tc->p[14], (int)c.tc->p[15]);
+      info[INFO_SUCCESS] = t2o <= (real)0.07; info[INFO_NEAR_OBJECT] = tcp_to_obj <= (real)0.03;
+      info[INFO_GRASP_SUCCESS] = touch && opened > 0 && (obj[2] - (real)0.02 > oi[2]);
+      info[INFO_GRASP_REWARD] = g; info[INFO_IN_PLACE] = in_place; info[INFO_OBJ_TO_TARGET] = t2o; info[INFO_UNSCALED] = r;
+    } break;
+    case T_SWEEP: case T_SWEEP_INTO: {   // sawyer_sweep_v3.py:68-90,228-266 ; sawyer_sweep_into_goal_v3.py:68-90,219-257
+      bool into = c.tc->task_id == T_SWEEP_INTO;
+      const real* obj = obs + 4; real opened = obs[3];
+      real oi[3] = {c.s->obj_init[0], c.s->obj_init[1], c.s->obj_init[2]};
+      real tg[3] = {target[0], target[1], into ? obj[2] : target[2]};
+      real o2t = dist3(obj, tg), tcp_to_obj = dist3(obj, tcp);
+      real in_place = tol_long_tail(o2t, 0, (real)0.05, dist3(oi, tg));
+      real g = into ? grip_caging(c, obj, (real)0.02, (real)0.005, (real)0.01) : grip_caging(c, obj, (real)0.02, (real)0.01, (real)0.005);
+      real r = 2 * g + 6 * hamacher(g, in_place);
+      if (o2t < (real)0.05) r = 10;
+      *reward = r;
+      bool touch = touching_object(c, c.tc->main_geom, (int)c.tc->p[14], (int)c.tc->p[15]);
+      info[INFO_SUCCESS] = o2t <= (real)0.05; info[INFO_NEAR_OBJECT] = tcp_to_obj <= (real)0.03; info[INFO_GRASP_SUCCESS] = touch && opened > 0;
+      info[INFO_GRASP_REWARD] = g; info[INFO_IN_PLACE] = in_place; info[INFO_OBJ_TO_TARGET] = o2t; info[INFO_UNSCALED] = r;
+    } break;
+    case T_HAND_INSERT: {   // sawyer_hand_insert_v3.py:67-95,129-175
+      const real* obj = obs + 4; real opened = obs[3];
+      real oi[3] = {c.s->obj_init[0], c.s->obj_init[1], c.s->obj_init[2]};
+      real t2o = dist3(obj, target), tcp_to_obj = dist3(obj, tcp);
+      real in_place = tol_long_tail(t2o, 0, (real)0.05, dist3(oi, target));
+      real g = gripper_caging_reward(c, obj, (real)0.015, (real)0.05, (real)0.01, (real)0.005, 1, 1);
+      real r = hamacher(g, in_place);
+      if (tcp_to_obj < (real)0.02 && opened > 0) r += 1 + 7 * in_place;
+      if (t2o < (real)0.05) r = 10;
+      *reward = r;
+      bool touch = touching_object(c, c.tc->main_geom, (int)c.tc->p[14], (int)c.tc->p[15]);
+      info[INFO_SUCCESS] = t2o <= (real)0.05; info[INFO_NEAR_OBJECT] = tcp_to_obj <= (real)0.03;
+      info[INFO_GRASP_SUCCESS] = touch && opened > 0 && (obj[2] - (real)0.02 > oi[2]);
+      info[INFO_GRASP_REWARD] = g; info[INFO_IN_PLACE] = in_place; info[INFO_OBJ_TO_TARGET] = t2o; info[INFO_UNSCALED] = r;
+    } break;
+    case T_PICK_OUT_OF_HOLE: {   // sawyer_pick_out_of_hole_v3.py:67-98,138-208
+      const real* obj = obs + 4;
+      real oi[3] = {c.s->obj_init[0], c.s->obj_init[1], c.s->obj_init[2]};
+      real o2t = dist3(obj, target), tcp_to_obj = dist3(obj, tcp);
+      real dx = tcp[0] - oi[0], dy = tcp[1] - oi[1], radius = sqrt(dx * dx + dy * dy);
+      real floorh = radius <= (real)0.03 ? (real)0 : (real)0.015 * log(radius - (real)0.03) + (real)0.15;
+      real above = tcp[2] >= floorh ? (real)1 : tol_long_tail(fmax(floorh - tcp[2], (real)0), 0, (real)0.01, (real)0.02);
+      real g = gripper_caging_reward(c, obj, (real)0.015, (real)0.02, (real)0.01, (real)0.03, (real)0.1, 1);
+      real in_place = tol_long_tail(o2t, 0, (real)0.02, dist3(oi, target));
+      real r = hamacher(g, in_place);
+      bool gs = tcp_to_obj < (real)0.04 && (obj[2] - (real)0.02 > oi[2]) && !(obs[3] < (real)0.33);
+      if (gs) r += 1 + 5 * hamacher(in_place, above);
+      if (o2t < (real)0.05) r = 10;
+      *reward = r;
+      info[INFO_SUCCESS] = o2t <= (real)0.07; info[INFO_NEAR_OBJECT] = tcp_to_obj <= (real)0.03; info[INFO_GRASP_SUCCESS] = gs;
+      info[INFO_GRASP_REWARD] = g; info[INFO_IN_PLACE] = in_place; info[INFO_OBJ_TO_TARGET] = o2t; info[INFO_UNSCALED] = r;
     } break;
     case T_PUSH: {   // sawyer_push_v3.py:85-113,171-213
       const real* obj = obs + 4; real opened = obs[3];
@@ -234,9 +337,35 @@ DEV void task_reset_model(const TaskCtx& c, const float* rv, int lane) {
       SYNCW();
       set_obj_xyz(c, p, lane);
     } break;
-    case T_PICK_PLACE: {   // sawyer_pick_place_v3.py:141-178
+    case T_PICK_PLACE: case T_REACH_WALL: case T_PICK_PLACE_WALL: case T_PICK_OUT_OF_HOLE: {   // obj = rv[:3], goal = rv[3:6]; _set_obj_xyz
       real p[3] = {rv[0], rv[1], rv[2]};
       if (lane == 0) for (int i = 0; i < 3; i++) { c.s->target[i] = rv[3 + i]; c.s->obj_init[i] = rv[i]; }
+      SYNCW();
+      set_obj_xyz(c, p, lane);
+    } break;
+    case T_PUSH_WALL: case T_PUSH_BACK: {   // sawyer_push_wall_v3.py:135-171 ; sawyer_push_back_v3.py:120-140: z = geom objGeom's current height
+      real og[3]; mw_frame_pos(c.m, c.w, F_TASK0 + 1, og);
+      real p[3] = {rv[0], rv[1], og[2]};
+      if (lane == 0) { c.s->target[0] = rv[3]; c.s->target[1] = rv[4]; c.s->target[2] = (float)og[2]; for (int i = 0; i < 3; i++) c.s->obj_init[i] = (float)p[i]; }
+      SYNCW();
+      set_obj_xyz(c, p, lane);
+    } break;
+    case T_SWEEP: {   // sawyer_sweep_v3.py:99-115: goal = (0.5, obj y, 0.01), obj z = 0.02
+      real p[3] = {rv[0], rv[1], (real)0.02};
+      if (lane == 0) { c.s->target[0] = 0.5f; c.s->target[1] = rv[1]; c.s->target[2] = 0.01f; for (int i = 0; i < 3; i++) c.s->obj_init[i] = (float)p[i]; }
+      SYNCW();
+      set_obj_xyz(c, p, lane);
+    } break;
+    case T_SWEEP_INTO: {   // sawyer_sweep_into_goal_v3.py:101-121: fixed goal (0, 0.84, 0.02); obj z = body obj's current height
+      real ob[3]; mw_frame_pos(c.m, c.w, F_TASK0, ob);
+      real p[3] = {rv[0], rv[1], ob[2]};
+      if (lane == 0) { c.s->target[0] = 0.f; c.s->target[1] = 0.84f; c.s->target[2] = 0.02f; for (int i = 0; i < 3; i++) c.s->obj_init[i] = (float)p[i]; }
+      SYNCW();
+      set_obj_xyz(c, p, lane);
+    } break;
+    case T_HAND_INSERT: {   // sawyer_hand_insert_v3.py:108-127: obj z stays 0.05
+      real p[3] = {rv[0], rv[1], (real)0.05};
+      if (lane == 0) for (int i = 0; i < 3; i++) { c.s->target[i] = rv[3 + i]; c.s->obj_init[i] = (float)p[i]; }
       SYNCW();
       set_obj_xyz(c, p, lane);
     } break;

@@ -16,7 +16,7 @@ from .tasks import TASKS, TaskSpec
 
 _LIB = None
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libmwb200.so")
+SO_PATH = os.environ.get("MW_B200_LIB") or os.path.join(_HERE, "libmwb200.so")   # MW_B200_LIB=.../libmwb200_f64.so selects the double build
 
 TASKCONST_DTYPE = np.dtype([("task_id", "i4"), ("nframe_task", "i4"), ("main_geom", "i4"), ("pad", "i4"),
                             ("hand_init", "f4", 3), ("mocap_lo", "f4", 3), ("mocap_hi", "f4", 3),
@@ -59,6 +59,7 @@ def lib():
         L.mw_set_state.argtypes = [vp, vp]
         L.mw_debug_substeps.argtypes = [vp, ip, vp, vp]
         L.mw_get_counters.argtypes = [vp, vp]
+        L.mw_debug_forward.argtypes = [vp, vp, vp, vp]
         assert L.mw_sizeof_model() == lower.DTYPE.itemsize, "MwModel layout mismatch (rebuild the library)"
         assert L.mw_sizeof_taskconst() == TASKCONST_DTYPE.itemsize
         assert L.mw_sizeof_envstate() == ENVSTATE_DTYPE.itemsize == 512
@@ -196,6 +197,16 @@ class Engine:
     def debug_substeps(self, nstep, ctrl=(0.0, 0.0)):
         c = np.array(ctrl, dtype=np.float32)
         _ck(lib().mw_debug_substeps(self.h, int(nstep), c.ctypes.data, self._stream()))
+
+    def debug_forward(self, ctrl=(0.0, 0.0)):
+        """One forward pass per env without changing state; returns (contacts[n, MAXCON, 12], qacc[n, MAXDOF], meta[n, 4])."""
+        nf = lib().mw_debug_dump_floats()
+        buf = self.torch.zeros(self.n_envs, nf, device=self.device)
+        c = np.array(ctrl, dtype=np.float32)
+        _ck(lib().mw_debug_forward(self.h, c.ctypes.data, self._p(buf), self._stream()))
+        a = buf.cpu().numpy()
+        ncw = (nf - 17 - 4)
+        return a[:, :ncw].reshape(self.n_envs, -1, 12), a[:, ncw:ncw + 17], a[:, ncw + 17:]
 
     def counters(self):
         out = np.zeros(5, dtype=np.uint64)

@@ -27,7 +27,7 @@ class TaskSpec:
     rand_hi: tuple
     goal_low: tuple              # goal_space (obs clipping)
     goal_high: tuple
-    reject: tuple | None = None  # ((a0,a1),(b0,b1),thr): redraw while |v[a0:a1]-v[b0:b1]| < thr
+    reject: tuple | None = None  # ((a0,a1),(b0,b1) or fixed point,thr): redraw while |v[a0:a1]-other| < thr
     main_geom: str | None = "objGeom"
     params: tuple = ()
 
@@ -86,6 +86,32 @@ _SPECS = [
              (-0.1, 0.7, 0.16), (0.1, 0.9, 0.16), _HL, _HH, main_geom=None),
     TaskSpec("window-close-v3", 9, "sawyer_window_horizontal", "window", [("site", "handleCloseStart")], (0, 0.4, 0.2), _HL, _HH,
              (0.0, 0.75, 0.2), (0.0, 0.9, 0.2), _HL, _HH, main_geom=None),
+    # ---- wall variants (sawyer_reach_wall_v3.py, sawyer_push_wall_v3.py, sawyer_pick_place_wall_v3.py)
+    TaskSpec("reach-wall-v3", 10, "sawyer_reach_wall_v3", None, _OBJ, _H0, _HL, _HH,
+             _cat((-0.05, 0.6, 0.015), (-0.05, 0.85, 0.05)), _cat((0.05, 0.65, 0.015), (0.05, 0.9, 0.3)),
+             (-0.05, 0.85, 0.05), (0.05, 0.9, 0.3), reject=(_XY[0], _XY[1], 0.15)),
+    TaskSpec("push-wall-v3", 11, "sawyer_push_wall_v3", None, _OBJ, _H0, _HL, _HH,
+             _cat((-0.05, 0.6, 0.015), (-0.05, 0.85, 0.01)), _cat((0.05, 0.65, 0.015), (0.05, 0.9, 0.02)),
+             (-0.05, 0.85, 0.01), (0.05, 0.9, 0.02), reject=(_XY[0], _XY[1], 0.15)),
+    TaskSpec("pick-place-wall-v3", 12, "sawyer_pick_place_wall_v3", None, _OBJ, _H0, _HL, _HH,
+             _cat((-0.05, 0.6, 0.015), (-0.05, 0.85, 0.05)), _cat((0.05, 0.65, 0.015), (0.05, 0.9, 0.3)),
+             (-0.05, 0.85, 0.05), (0.05, 0.9, 0.3), reject=(_XY[0], _XY[1], 0.15)),
+    # ---- sawyer_push_back_v3.py, sawyer_sweep_v3.py, sawyer_sweep_into_goal_v3.py
+    TaskSpec("push-back-v3", 13, "sawyer_push_back_v3", None, _OBJ, _H0, _HL, _HH,
+             _cat((-0.1, 0.8, 0.02), (-0.1, 0.6, 0.0199)), _cat((0.1, 0.85, 0.02), (0.1, 0.7, 0.0201)),
+             (-0.1, 0.6, 0.0199), (0.1, 0.7, 0.0201), reject=(_XY[0], _XY[1], 0.15)),
+    TaskSpec("sweep-v3", 14, "sawyer_sweep_v3", None, _OBJ, _H0, _HL, _HH,
+             (-0.1, 0.6, 0.02), (0.1, 0.7, 0.02), (0.49, 0.6, 0.00), (0.51, 0.7, 0.02)),
+    TaskSpec("sweep-into-v3", 15, "sawyer_table_with_hole", None, _OBJ, _H0, _HL, _HH,
+             _cat((-0.1, 0.6, 0.02), (-0.001, 0.8399, 0.0199)), _cat((0.1, 0.7, 0.02), (0.001, 0.8401, 0.0201)),
+             (-0.001, 0.8399, 0.0199), (0.001, 0.8401, 0.0201), reject=((0, 2), (0.0, 0.84), 0.15)),
+    # ---- sawyer_hand_insert_v3.py, sawyer_pick_out_of_hole_v3.py
+    TaskSpec("hand-insert-v3", 16, "sawyer_table_with_hole", None, _OBJ, _H0, (-0.5, 0.40, -0.15), _HH,
+             _cat((-0.1, 0.6, 0.05), (-0.04, 0.8, -0.0201)), _cat((0.1, 0.7, 0.05), (0.04, 0.88, -0.0199)),
+             (-0.04, 0.8, -0.0201), (0.04, 0.88, -0.0199), reject=(_XY[0], _XY[1], 0.15)),
+    TaskSpec("pick-out-of-hole-v3", 17, "sawyer_pick_out_of_hole", None, _OBJ, _H0, (-0.5, 0.40, -0.05), _HH,
+             _cat((0, 0.75, 0.02), (-0.1, 0.5, 0.15)), _cat((0, 0.75, 0.02), (0.1, 0.6, 0.3)),
+             (-0.1, 0.5, 0.15), (0.1, 0.6, 0.3), reject=(_XY[0], _XY[1], 0.15)),
 ]
 
 TASKS = {t.name: t for t in _SPECS}

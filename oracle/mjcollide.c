@@ -473,8 +473,8 @@ static void simplex_weights(const SV* s, int n, double* w) {
   closest_tri(s[0].v, s[1].v, s[2].v, w);
 }
 
-#define EPA_MAXV 96
-#define EPA_MAXF 192
+#define EPA_MAXV 160
+#define EPA_MAXF 320
 typedef struct { int v[3]; double n[3], d; int alive; } EFace;
 
 static int epa_add_face(EFace* F, int* nf, const SV* V, int a, int b, int c) {
@@ -524,7 +524,7 @@ static int epa(const Shape* A, const Shape* B, SV* s, int n, RawCon* o, double* 
   for (int i = 0; i < 4; i++) V[nv++] = s[i];
   epa_add_face(F, &nf, V, 0, 1, 2); epa_add_face(F, &nf, V, 0, 2, 3); epa_add_face(F, &nf, V, 0, 3, 1); epa_add_face(F, &nf, V, 1, 3, 2);
   int bestf = -1;
-  for (int it = 0; it < 64; it++) {
+  for (int it = 0; it < 176; it++) {
     bestf = -1; double bd = 1e300;
     for (int f = 0; f < nf; f++) if (F[f].alive && F[f].d < bd) { bd = F[f].d; bestf = f; }
     if (bestf < 0) return 0;
@@ -565,28 +565,74 @@ static int epa(const Shape* A, const Shape* B, SV* s, int n, RawCon* o, double* 
 }
 
 
-/* Face-on contact of a cylinder cap with a box face: every point of the overlap patch is a valid EPA witness, so
-   the contact point is implementation-defined.  We take the pressure centroid of the (linearly penetrating) cap:
-   offset r^2 sin(tilt) / (4 p0) from the cap centre towards the deepest rim point (p0 = penetration of the cap
-   centre), clamped to the rim.  Leaves every other configuration untouched. */
+/* Face-on contact between a cylinder and a box face (cap-on-face or generator-line-on-face): every point of the
+   contact patch is a valid EPA witness, so the contact *point* is implementation-defined in the reference physics.
+   We take the pressure centroid of the patch under a linear penetration profile, clipped to the overlap with the
+   box face (continuous in the pose; removes rim-to-rim chatter of resting cylinders).  Other configurations are
+   left as EPA/GJK produced them. */
 static void refine_cyl_box(const Shape* A, const Shape* B, RawCon* o) {
   if (A->type != G_CYLINDER || B->type != G_BOX) return;
-  double nl[3], nb[3]; mat_tmulvec(nl, A->mat, o->normal); mat_tmulvec(nb, B->mat, o->normal);
-  if (fabs(nl[2]) < 0.9) return;
-  int k = 0; for (int i = 1; i < 3; i++) if (fabs(nb[i]) > fabs(nb[k])) k = i;
-  if (fabs(nb[k]) < 0.99999) return;
-  double r = A->size[0], depth = -o->dist, rad = sqrt(nl[0] * nl[0] + nl[1] * nl[1]);
-  double p0 = depth - r * rad;
-  if (p0 <= 0) return;
-  double sbar = rad > 1e-12 ? fmin(r, r * r * rad / (4 * p0)) : 0.0;
-  double pl[3] = {0, 0, nl[2] > 0 ? A->size[1] : -A->size[1]}, pw[3], t[3], pb[3];
-  if (rad > 1e-12) { pl[0] = nl[0] / rad * sbar; pl[1] = nl[1] / rad * sbar; }
-  mat_mulvec(pw, A->mat, pl); v3add(pw, pw, A->pos);
-  v3sub(t, pw, B->pos); mat_tmulvec(pb, B->mat, t);
-  for (int i = 0; i < 3; i++) if (i != k && fabs(pb[i]) > B->size[i]) return;
-  double pen = p0 + sbar * rad;
+  double nb[3]; mat_tmulvec(nb, B->mat, o->normal);
+  int k = 0; for (int q = 1; q < 3; q++) if (fabs(nb[q]) > fabs(nb[k])) k = q;
+  if (fabs(nb[k]) < 0.99999) return;                       /* the contact normal must be a face normal of the box */
+  const double sgn = nb[k] > 0 ? 1 : -1;
+  const int i = (k + 1) % 3, j = (k + 2) % 3;
+  const double r = A->size[0], h = A->size[1];
+  double ax[3], a[3], t[3], cB[3];
+  mat_col(ax, A->mat, 2); mat_tmulvec(a, B->mat, ax);
+  v3sub(t, A->pos, B->pos); mat_tmulvec(cB, B->mat, t);
+  const double ak = a[k] * sgn;
+  double P[3], pen;
+  if (fabs(ak) > 0.9) {
+    /* ---- cap on face */
+    const double cs = ak > 0 ? 1 : -1;
+    double C[3], acap[3], g[3];
+    for (int q = 0; q < 3; q++) { acap[q] = cs * a[q]; C[q] = cB[q] + cs * h * a[q]; }
+    const double pen0 = sgn * C[k] + B->size[k];
+    for (int q = 0; q < 3; q++) g[q] = -(sgn * acap[k]) * acap[q];
+    g[k] += sgn;
+    const double st = v3norm(g);                                   /* sin(tilt) */
+    double sbar = 0;
+    if (st > 1e-9) sbar = pen0 > 0 ? fmin(r, r * r * st / (4 * pen0)) : r;
+    for (int q = 0; q < 3; q++) P[q] = C[q] + (st > 1e-9 ? g[q] / st * sbar : 0);
+    const int axs[2] = {i, j};
+    for (int q = 0; q < 2; q++) {
+      const int u = axs[q];
+      const double lo = fmax(C[u] - r, -B->size[u]), hi = fmin(C[u] + r, B->size[u]);
+      if (lo > hi) return;
+      P[u] = fmin(fmax(P[u], lo), hi);
+    }
+    P[k] = C[k] - (acap[i] * (P[i] - C[i]) + acap[j] * (P[j] - C[j])) / acap[k];
+    pen = sgn * P[k] + B->size[k];
+  } else if (fabs(ak) < 0.1) {
+    /* ---- generator line on face */
+    double d[3], L0[3];
+    for (int q = 0; q < 3; q++) d[q] = -(sgn * a[k]) * a[q];
+    d[k] += sgn;
+    v3normalize(d);
+    for (int q = 0; q < 3; q++) L0[q] = cB[q] + r * d[q];
+    double t0 = -h, t1 = h;
+    const int axs[2] = {i, j};
+    for (int q = 0; q < 2; q++) {
+      const int u = axs[q];
+      if (fabs(a[u]) > 1e-9) {
+        const double ta = (-B->size[u] - L0[u]) / a[u], tb = (B->size[u] - L0[u]) / a[u];
+        t0 = fmax(t0, fmin(ta, tb)); t1 = fmin(t1, fmax(ta, tb));
+      } else if (fabs(L0[u]) > B->size[u]) return;
+    }
+    if (t0 > t1) return;
+    const double tm = 0.5 * (t0 + t1), Lh = 0.5 * (t1 - t0), sl = sgn * a[k];
+    const double penm = sgn * (L0[k] + tm * a[k]) + B->size[k];
+    double off;
+    if (penm > 0) off = fmin(fmax(sl * Lh * Lh / (3 * penm), -Lh), Lh);
+    else off = sl > 0 ? Lh : (sl < 0 ? -Lh : 0);
+    const double ts = tm + off;
+    for (int q = 0; q < 3; q++) P[q] = L0[q] + ts * a[q];
+    pen = sgn * P[k] + B->size[k];
+  } else return;
   o->dist = -pen;
-  v3addscl(o->pos, pw, o->normal, -0.5 * pen);
+  P[k] -= sgn * 0.5 * pen;
+  mat_mulvec(o->pos, B->mat, P); v3add(o->pos, o->pos, B->pos);
 }
 
 static int convex_convex(const Shape* A, const Shape* B, double margin, RawCon* o) {
@@ -603,7 +649,7 @@ static int convex_convex(const Shape* A, const Shape* B, double margin, RawCon* 
     SV w; support(A, B, nd, &w);
     double vw = v3dot(v, w.v);
     if (vv - vw <= 1e-12 * vv) break; /* no progress: v is the closest point */
-    if (sqrt(vv) - ra - rb > margin && vw > 0 && vw / sqrt(vv) - ra - rb > margin) return 0; /* separating axis */
+    if (vw > 0 && vw / sqrt(vv) - ra - rb > margin + 1e-4) return 0; /* separating axis */
     int dup = 0;
     for (int i = 0; i < n; i++) { double t[3]; v3sub(t, s[i].v, w.v); if (v3dot(t, t) < 1e-24) dup = 1; }
     if (dup) break;
@@ -619,12 +665,13 @@ static int convex_convex(const Shape* A, const Shape* B, double margin, RawCon* 
     double dcore = v3norm(dvec);
     if (dcore > 1e-10) {
       double dist = dcore - ra - rb;
-      if (dist > margin) return 0;
+      if (dist > margin + 1e-4) return 0;      /* slack: the analytic refinement below makes the final call */
       v3scl(o->normal, dvec, 1 / dcore);
       o->dist = dist;
       double sa[3], sb[3]; v3addscl(sa, wa, o->normal, ra); v3addscl(sb, wb, o->normal, -rb);
       for (int k = 0; k < 3; k++) o->pos[k] = 0.5 * (sa[k] + sb[k]);
-      return 1;
+      refine_cyl_box(A, B, o);
+      return o->dist <= margin;
     }
     enclosed = 1;
   }
@@ -636,7 +683,7 @@ static int convex_convex(const Shape* A, const Shape* B, double margin, RawCon* 
   double sa[3], sb[3]; v3addscl(sa, wa, o->normal, ra); v3addscl(sb, wb, o->normal, -rb);
   for (int k = 0; k < 3; k++) o->pos[k] = 0.5 * (sa[k] + sb[k]);
   refine_cyl_box(A, B, o);
-  return 1;
+  return o->dist <= margin;
 }
 
 /* ------------------------------------------------------------------ driver */

@@ -598,6 +598,432 @@ class WindowClose(_Window):
         return self._get_obs()
 
 
+
+class _GeomObjMixin:
+    """Object observed through geom 'objGeom' (push-wall / pick-place-wall / push-back)."""
+
+    def _get_pos_objects(self):
+        return self.data.geom("objGeom").xpos
+
+    def _get_quat_objects(self):
+        return mat2quat_xyzw(self.data.geom("objGeom").xmat)
+
+    def adjust_initObjPos(self, orig):
+        diff = self.get_body_com("obj")[:2] - self.data.geom("objGeom").xpos[:2]
+        adj = orig[:2] + diff
+        return A([adj[0], adj[1], self.data.geom("objGeom").xpos[-1]])
+
+
+def _grip_caging(env, action, obj_pos, obj_radius, grip_add, xz_margin_c):
+    """Task-local caging override shared by push-back / sweep / sweep-into / soccer
+    (e.g. sawyer_push_back_v3.py:160-254): y-caging and y-gripping from the live pad positions."""
+    pad_success_margin = 0.05
+    grip_success_margin = obj_radius + grip_add
+    tcp = env.tcp_center
+    left_pad, right_pad = env.get_body_com("leftpad"), env.get_body_com("rightpad")
+    dl, dr = left_pad[1] - obj_pos[1], obj_pos[1] - right_pad[1]
+    rm = abs(abs(obj_pos[1] - env.init_right_pad[1]) - pad_success_margin)
+    lm = abs(abs(obj_pos[1] - env.init_left_pad[1]) - pad_success_margin)
+    rc = tolerance(dr, bounds=(obj_radius, pad_success_margin), margin=rm, sigmoid="long_tail")
+    lc = tolerance(dl, bounds=(obj_radius, pad_success_margin), margin=lm, sigmoid="long_tail")
+    rg = tolerance(dr, bounds=(obj_radius, grip_success_margin), margin=rm, sigmoid="long_tail")
+    lg = tolerance(dl, bounds=(obj_radius, grip_success_margin), margin=lm, sigmoid="long_tail")
+    y_caging = hamacher_product(rc, lc)
+    y_gripping = hamacher_product(rg, lg)
+    xz = [0, 2]
+    margin = norm(A(env.obj_init_pos)[xz] - env.init_tcp[xz]) - xz_margin_c
+    x_z_caging = tolerance(float(norm(tcp[xz] - obj_pos[xz])), bounds=(0, xz_margin_c), margin=margin, sigmoid="long_tail")
+    caging = hamacher_product(y_caging, x_z_caging)
+    gripping = y_gripping if caging > 0.95 else 0.0
+    return (caging + gripping) / 2
+
+
+class ReachWall(Reach):
+    """metaworld/envs/sawyer_reach_wall_v3.py"""
+    xml = "sawyer_reach_wall_v3"
+    obj_low, obj_high = (-0.05, 0.6, 0.015), (0.05, 0.65, 0.015)
+    goal_low, goal_high = (-0.05, 0.85, 0.05), (0.05, 0.9, 0.3)
+
+    def setup(self):
+        self.init_config = dict(obj_init_pos=A([0, 0.6, 0.02]), hand_init_pos=A([0, 0.6, 0.2]))
+        self.goal = A([-0.05, 0.8, 0.2])
+        self.obj_init_pos = self.init_config["obj_init_pos"]
+        self.hand_init_pos = self.init_config["hand_init_pos"]
+
+    def reset_model(self):
+        self._reset_hand()
+        goal_pos = self._get_state_rand_vec()
+        self._target_pos = goal_pos[-3:]
+        self.obj_init_pos = goal_pos[:3]
+        self._set_obj_xyz(self.obj_init_pos)
+        self.model.site("goal").pos = self._target_pos
+        return self._get_obs()
+
+    def evaluate_state(self, obs, action):
+        reward, tcp_to_object, in_place = self.compute_reward(action, obs)
+        return reward, dict(success=float(tcp_to_object <= 0.05), near_object=0.0, grasp_success=0.0, grasp_reward=0.0,
+                            in_place_reward=in_place, obj_to_target=tcp_to_object, unscaled_reward=reward)
+
+
+class PushWall(_GeomObjMixin, SawyerXYZEnv):
+    """metaworld/envs/sawyer_push_wall_v3.py"""
+    xml = "sawyer_push_wall_v3"
+    hand_low, hand_high = (-0.5, 0.40, 0.05), (0.5, 1, 0.5)
+    obj_low, obj_high = (-0.05, 0.6, 0.015), (0.05, 0.65, 0.015)
+    goal_low, goal_high = (-0.05, 0.85, 0.01), (0.05, 0.9, 0.02)
+    midpoint_scale = (3.0, 1.0, 1.0)
+
+    def setup(self):
+        self.init_config = dict(obj_init_pos=A([0, 0.6, 0.02]), hand_init_pos=A([0, 0.6, 0.2]))
+        self.obj_init_pos = self.init_config["obj_init_pos"]
+        self.hand_init_pos = self.init_config["hand_init_pos"]
+
+    def random_reset_space(self):
+        return np.hstack((self.obj_low, self.goal_low)), np.hstack((self.obj_high, self.goal_high))
+
+    def reset_model(self):
+        self._reset_hand()
+        self.obj_init_pos = self.adjust_initObjPos(self.init_config["obj_init_pos"])
+        goal_pos = self._get_state_rand_vec()
+        self._target_pos = np.concatenate([goal_pos[-3:-1], [self.obj_init_pos[-1]]])
+        self.obj_init_pos = np.concatenate([goal_pos[:2], [self.obj_init_pos[-1]]])
+        self.model.site("goal").pos = self._target_pos
+        self._set_obj_xyz(self.obj_init_pos)
+        return self._get_obs()
+
+    def evaluate_state(self, obs, action):
+        obj = obs[4:7]
+        reward, tcp_to_obj, tcp_open, obj_to_target, grasp_reward, in_place_reward = self.compute_reward(action, obs)
+        grasp_success = float(self.touching_main_object and (tcp_open > 0) and (obj[2] - 0.02 > self.obj_init_pos[2]))
+        return reward, dict(success=float(obj_to_target <= 0.07), near_object=float(tcp_to_obj <= 0.03), grasp_success=grasp_success,
+                            grasp_reward=grasp_reward, in_place_reward=in_place_reward, obj_to_target=obj_to_target, unscaled_reward=reward)
+
+    def compute_reward(self, action, obs):
+        tcp, obj, tcp_opened, target = self.tcp_center, obs[4:7], obs[3], self._target_pos
+        midpoint = A([-0.05, 0.77, obj[2]])
+        tcp_to_obj = float(norm(obj - tcp))
+        sc = A(self.midpoint_scale)
+        o2m = float(norm((obj - midpoint) * sc))
+        o2m_init = float(norm((self.obj_init_pos - midpoint) * sc))
+        o2t = float(norm(obj - target))
+        o2t_init = float(norm(self.obj_init_pos - target))
+        p1 = tolerance(o2m, bounds=(0, 0.05), margin=o2m_init, sigmoid="long_tail")
+        p2 = tolerance(o2t, bounds=(0, 0.05), margin=o2t_init, sigmoid="long_tail")
+        g = self._gripper_caging_reward(action, obj, object_reach_radius=0.01, obj_radius=0.015, pad_success_thresh=0.05,
+                                        xz_thresh=0.005, high_density=True)
+        reward = 2 * g
+        if tcp_to_obj < 0.02 and tcp_opened > 0:
+            reward = 2.0 * g + 1.0 + 4.0 * p1
+            if obj[1] > 0.75:
+                reward = 2 * g + 1.0 + 4.0 + 3.0 * p2
+        if o2t < 0.05:
+            reward = 10.0
+        return reward, tcp_to_obj, tcp_opened, o2t, g, p2
+
+
+class PickPlaceWall(_GeomObjMixin, SawyerXYZEnv):
+    """metaworld/envs/sawyer_pick_place_wall_v3.py"""
+    xml = "sawyer_pick_place_wall_v3"
+    hand_low, hand_high = (-0.5, 0.40, 0.05), (0.5, 1, 0.5)
+    obj_low, obj_high = (-0.05, 0.6, 0.015), (0.05, 0.65, 0.015)
+    goal_low, goal_high = (-0.05, 0.85, 0.05), (0.05, 0.9, 0.3)
+
+    def setup(self):
+        self.init_config = dict(obj_init_pos=A([0, 0.6, 0.02]), hand_init_pos=A([0, 0.6, 0.2]))
+        self.obj_init_pos = self.init_config["obj_init_pos"]
+        self.hand_init_pos = self.init_config["hand_init_pos"]
+
+    def random_reset_space(self):
+        return np.hstack((self.obj_low, self.goal_low)), np.hstack((self.obj_high, self.goal_high))
+
+    def reset_model(self):
+        self._reset_hand()
+        goal_pos = self._get_state_rand_vec()
+        self._target_pos = goal_pos[-3:]
+        self.obj_init_pos = goal_pos[:3]
+        self._set_obj_xyz(self.obj_init_pos)
+        self.model.site("goal").pos = self._target_pos
+        return self._get_obs()
+
+    evaluate_state = PushWall.evaluate_state
+
+    def compute_reward(self, action, obs):
+        tcp, obj, tcp_opened, target = self.tcp_center, obs[4:7], obs[3], self._target_pos
+        midpoint = A([self._target_pos[0], 0.77, 0.25])
+        tcp_to_obj = float(norm(obj - tcp))
+        sc = A([1.0, 1.0, 3.0])
+        o2m = float(norm((obj - midpoint) * sc))
+        o2m_init = float(norm((self.obj_init_pos - midpoint) * sc))
+        o2t = float(norm(obj - target))
+        o2t_init = float(norm(self.obj_init_pos - target))
+        p1 = tolerance(o2m, bounds=(0, 0.05), margin=o2m_init, sigmoid="long_tail")
+        p2 = tolerance(o2t, bounds=(0, 0.05), margin=o2t_init, sigmoid="long_tail")
+        g = self._gripper_caging_reward(action=action, obj_pos=obj, obj_radius=0.015, pad_success_thresh=0.05, object_reach_radius=0.01,
+                                        xz_thresh=0.005, high_density=False)
+        ipg = hamacher_product(g, p1)
+        reward = ipg
+        if tcp_to_obj < 0.02 and (tcp_opened > 0) and (obj[2] - 0.015 > self.obj_init_pos[2]):
+            reward = ipg + 1.0 + 4.0 * p1
+            if obj[1] > 0.75:
+                reward = ipg + 1.0 + 4.0 + 3.0 * p2
+        if o2t < 0.05:
+            reward = 10.0
+        return reward, tcp_to_obj, tcp_opened, o2t, g, p2
+
+
+class PushBack(_GeomObjMixin, SawyerXYZEnv):
+    """metaworld/envs/sawyer_push_back_v3.py"""
+    xml = "sawyer_push_back_v3"
+    hand_low, hand_high = (-0.5, 0.40, 0.05), (0.5, 1, 0.5)
+    obj_low, obj_high = (-0.1, 0.8, 0.02), (0.1, 0.85, 0.02)
+    goal_low, goal_high = (-0.1, 0.6, 0.0199), (0.1, 0.7, 0.0201)
+    OBJ_RADIUS, TARGET_RADIUS = 0.007, 0.05
+
+    def setup(self):
+        self.init_config = dict(obj_init_pos=A([0, 0.8, 0.02]), hand_init_pos=A([0, 0.6, 0.2], dtype=np.float32))
+        self.obj_init_pos = self.init_config["obj_init_pos"]
+        self.hand_init_pos = self.init_config["hand_init_pos"]
+
+    def random_reset_space(self):
+        return np.hstack((self.obj_low, self.goal_low)), np.hstack((self.obj_high, self.goal_high))
+
+    def reset_model(self):
+        self._reset_hand()
+        self.obj_init_pos = self.adjust_initObjPos(self.init_config["obj_init_pos"])
+        goal_pos = self._get_state_rand_vec()
+        self._target_pos = np.concatenate([goal_pos[-3:-1], [self.obj_init_pos[-1]]])
+        self.obj_init_pos = np.concatenate([goal_pos[:2], [self.obj_init_pos[-1]]])
+        self._set_obj_xyz(self.obj_init_pos)
+        self.model.site("goal").pos = self._target_pos
+        return self._get_obs()
+
+    def evaluate_state(self, obs, action):
+        obj = obs[4:7]
+        reward, tcp_to_obj, tcp_opened, target_to_obj, object_grasped, in_place = self.compute_reward(action, obs)
+        grasp_success = float(self.touching_main_object and (tcp_opened > 0) and (obj[2] - 0.02 > self.obj_init_pos[2]))
+        return reward, dict(success=float(target_to_obj <= 0.07), near_object=float(tcp_to_obj <= 0.03), grasp_success=grasp_success,
+                            grasp_reward=object_grasped, in_place_reward=in_place, obj_to_target=target_to_obj, unscaled_reward=reward)
+
+    def compute_reward(self, action, obs):
+        obj, tcp_opened = obs[4:7], obs[3]
+        tcp_to_obj = float(norm(obj - self.tcp_center))
+        t2o = float(norm(obj - self._target_pos))
+        t2o_init = float(norm(self.obj_init_pos - self._target_pos))
+        in_place = tolerance(t2o, bounds=(0, self.TARGET_RADIUS), margin=t2o_init, sigmoid="long_tail")
+        g = _grip_caging(self, action, obj, self.OBJ_RADIUS, 0.003, 0.01)
+        reward = hamacher_product(g, in_place)
+        if (tcp_to_obj < 0.01) and (0 < tcp_opened < 0.55) and (t2o_init - t2o > 0.01):
+            reward += 1.0 + 5.0 * in_place
+        if t2o < self.TARGET_RADIUS:
+            reward = 10.0
+        return reward, tcp_to_obj, tcp_opened, t2o, g, in_place
+
+
+class Sweep(SawyerXYZEnv):
+    """metaworld/envs/sawyer_sweep_v3.py"""
+    xml = "sawyer_sweep_v3"
+    hand_low, hand_high = (-0.5, 0.40, 0.05), (0.5, 1.0, 0.5)
+    obj_low, obj_high = (-0.1, 0.6, 0.02), (0.1, 0.7, 0.02)
+    goal_low, goal_high = (0.49, 0.6, 0.00), (0.51, 0.7, 0.02)
+    OBJ_RADIUS = 0.02
+    grip_add, xz_c = 0.01, 0.005
+
+    def setup(self):
+        self.init_config = dict(obj_init_pos=A([0.0, 0.6, 0.02]), hand_init_pos=A([0.0, 0.6, 0.2]))
+        self.goal = A([0.5, 0.65, 0.01])
+        self.obj_init_pos = self.init_config["obj_init_pos"]
+        self.hand_init_pos = self.init_config["hand_init_pos"]
+
+    def random_reset_space(self):
+        return A(self.obj_low), A(self.obj_high)
+
+    def _get_pos_objects(self):
+        return self.data.body("obj").xpos
+
+    def _get_quat_objects(self):
+        return self.data.body("obj").xquat
+
+    def reset_model(self):
+        self._reset_hand()
+        self._target_pos = self.goal.copy()
+        self.obj_init_pos = self.init_config["obj_init_pos"]
+        obj_pos = self._get_state_rand_vec()
+        self.obj_init_pos = np.concatenate([obj_pos[:2], [self.obj_init_pos[-1]]])
+        self._target_pos[1] = obj_pos.copy()[1]
+        self._set_obj_xyz(self.obj_init_pos)
+        self.model.site("goal").pos = self._target_pos
+        return self._get_obs()
+
+    def evaluate_state(self, obs, action):
+        reward, tcp_to_obj, tcp_opened, target_to_obj, object_grasped, in_place = self.compute_reward(action, obs)
+        grasp_success = float(self.touching_main_object and (tcp_opened > 0))
+        return reward, dict(success=float(target_to_obj <= 0.05), near_object=float(tcp_to_obj <= 0.03), grasp_reward=object_grasped,
+                            grasp_success=grasp_success, in_place_reward=in_place, obj_to_target=target_to_obj, unscaled_reward=reward)
+
+    def target_for(self, obj):
+        return self._target_pos
+
+    def compute_reward(self, action, obs):
+        tcp, obj, tcp_opened = self.tcp_center, obs[4:7], obs[3]
+        target = self.target_for(obj)
+        o2t = float(norm(obj - target))
+        tcp_to_obj = float(norm(obj - tcp))
+        in_place = tolerance(o2t, bounds=(0, 0.05), margin=norm(self.obj_init_pos - target), sigmoid="long_tail")
+        g = _grip_caging(self, action, obj, self.OBJ_RADIUS, self.grip_add, self.xz_c)
+        reward = (2 * g) + (6 * hamacher_product(g, in_place))
+        if o2t < 0.05:
+            reward = 10.0
+        return reward, tcp_to_obj, tcp_opened, o2t, g, in_place
+
+
+class SweepInto(_FreeObjMixin, Sweep):
+    """metaworld/envs/sawyer_sweep_into_goal_v3.py"""
+    xml = "sawyer_table_with_hole"
+    hand_low, hand_high = (-0.5, 0.40, 0.05), (0.5, 1, 0.5)
+    obj_low, obj_high = (-0.1, 0.6, 0.02), (0.1, 0.7, 0.02)
+    goal_low, goal_high = (-0.001, 0.8399, 0.0199), (0.001, 0.8401, 0.0201)
+    grip_add, xz_c = 0.005, 0.01
+
+    def setup(self):
+        self.goal = A([0.0, 0.84, 0.02])
+        self.obj_init_pos = [0.0, 0.6, 0.02]
+        self.hand_init_pos = A([0.0, 0.6, 0.2])
+
+    def random_reset_space(self):
+        return np.hstack((self.obj_low, self.goal_low)), np.hstack((self.obj_high, self.goal_high))
+
+    def reset_model(self):
+        self._reset_hand()
+        self._target_pos = self.goal.copy()
+        self.obj_init_pos = self.get_body_com("obj")
+        goal_pos = self._get_state_rand_vec()
+        while norm(goal_pos[:2] - self._target_pos[:2]) < 0.15:
+            goal_pos = self._get_state_rand_vec()
+        self.obj_init_pos = np.concatenate([goal_pos[:2], [self.obj_init_pos[-1]]])
+        self._set_obj_xyz(self.obj_init_pos)
+        self.model.site("goal").pos = self._target_pos
+        return self._get_obs()
+
+    def target_for(self, obj):
+        return A([self._target_pos[0], self._target_pos[1], obj[2]])
+
+
+class HandInsert(SawyerXYZEnv):
+    """metaworld/envs/sawyer_hand_insert_v3.py"""
+    xml = "sawyer_table_with_hole"
+    hand_low, hand_high = (-0.5, 0.40, -0.15), (0.5, 1, 0.5)
+    obj_low, obj_high = (-0.1, 0.6, 0.05), (0.1, 0.7, 0.05)
+    goal_low, goal_high = (-0.04, 0.8, -0.0201), (0.04, 0.88, -0.0199)
+
+    def setup(self):
+        self.obj_init_pos = A([0, 0.6, 0.05])
+        self.hand_init_pos = A([0, 0.6, 0.2], dtype=np.float32)
+
+    def random_reset_space(self):
+        return np.hstack((self.obj_low, self.goal_low)), np.hstack((self.obj_high, self.goal_high))
+
+    def _get_pos_objects(self):
+        return self.get_body_com("obj")
+
+    def _get_quat_objects(self):
+        return self.data.body("obj").xquat
+
+    def reset_model(self):
+        self._reset_hand()
+        goal_pos = self._get_state_rand_vec()
+        while norm(goal_pos[:2] - goal_pos[-3:-1]) < 0.15:
+            goal_pos = self._get_state_rand_vec()
+        self.obj_init_pos = np.concatenate([goal_pos[:2], [self.obj_init_pos[-1]]])
+        self._target_pos = goal_pos[-3:]
+        self._set_obj_xyz(self.obj_init_pos)
+        self.model.site("goal").pos = self._target_pos
+        return self._get_obs()
+
+    def evaluate_state(self, obs, action):
+        obj = obs[4:7]
+        reward, tcp_to_obj, tcp_open, obj_to_target, grasp_reward, in_place_reward = self.compute_reward(action, obs)
+        gs = float(self.touching_main_object and (tcp_open > 0) and (obj[2] - 0.02 > self.obj_init_pos[2]))
+        return reward, dict(success=float(obj_to_target <= 0.05), near_object=float(tcp_to_obj <= 0.03), grasp_success=gs,
+                            grasp_reward=grasp_reward, in_place_reward=in_place_reward, obj_to_target=obj_to_target, unscaled_reward=reward)
+
+    def compute_reward(self, action, obs):
+        obj = obs[4:7]
+        t2o = float(norm(obj - self._target_pos))
+        t2o_init = float(norm(self.obj_init_pos - self._target_pos))
+        in_place = tolerance(t2o, bounds=(0, self.TARGET_RADIUS), margin=t2o_init, sigmoid="long_tail")
+        g = self._gripper_caging_reward(action, obj, object_reach_radius=0.01, obj_radius=0.015, pad_success_thresh=0.05, xz_thresh=0.005,
+                                        high_density=True)
+        reward = hamacher_product(g, in_place)
+        tcp_opened = obs[3]
+        tcp_to_obj = float(norm(obj - self.tcp_center))
+        if tcp_to_obj < 0.02 and tcp_opened > 0:
+            reward += 1.0 + 7.0 * in_place
+        if t2o < self.TARGET_RADIUS:
+            reward = 10.0
+        return reward, tcp_to_obj, tcp_opened, t2o, g, in_place
+
+
+class PickOutOfHole(SawyerXYZEnv):
+    """metaworld/envs/sawyer_pick_out_of_hole_v3.py"""
+    xml = "sawyer_pick_out_of_hole"
+    hand_low, hand_high = (-0.5, 0.40, -0.05), (0.5, 1, 0.5)
+    obj_low, obj_high = (0, 0.75, 0.02), (0, 0.75, 0.02)
+    goal_low, goal_high = (-0.1, 0.5, 0.15), (0.1, 0.6, 0.3)
+
+    def setup(self):
+        self.obj_init_pos = None
+        self.hand_init_pos = A([0.0, 0.6, 0.2])
+
+    def random_reset_space(self):
+        return np.hstack((self.obj_low, self.goal_low)), np.hstack((self.obj_high, self.goal_high))
+
+    @property
+    def _target_site_config(self):
+        return [("goal", self.obj_init_pos if self.obj_init_pos is not None else self.init_right_pad)]
+
+    def _get_pos_objects(self):
+        return self.get_body_com("obj")
+
+    def _get_quat_objects(self):
+        return self.data.body("obj").xquat
+
+    def reset_model(self):
+        self._reset_hand()
+        pos_obj, pos_goal = np.split(self._get_state_rand_vec(), 2)
+        self.obj_init_pos = pos_obj
+        self._set_obj_xyz(self.obj_init_pos)
+        self._target_pos = pos_goal
+        self.model.site("goal").pos = self._target_pos
+        return self._get_obs()
+
+    def evaluate_state(self, obs, action):
+        reward, tcp_to_obj, grasp_success, obj_to_target, grasp_reward, in_place_reward = self.compute_reward(action, obs)
+        return reward, dict(success=float(obj_to_target <= 0.07), near_object=float(tcp_to_obj <= 0.03), grasp_success=float(grasp_success),
+                            grasp_reward=grasp_reward, in_place_reward=in_place_reward, obj_to_target=obj_to_target, unscaled_reward=reward)
+
+    def compute_reward(self, action, obs):
+        obj, gripper = obs[4:7], self.tcp_center
+        o2t = float(norm(obj - self._target_pos))
+        tcp_to_obj = float(norm(obj - gripper))
+        in_place_margin = float(norm(self.obj_init_pos - self._target_pos))
+        threshold = 0.03
+        radius = float(norm(gripper[:2] - self.obj_init_pos[:2]))
+        floor = 0.0 if radius <= threshold else 0.015 * np.log(radius - threshold) + 0.15
+        above_floor = 1.0 if gripper[2] >= floor else tolerance(max(floor - gripper[2], 0.0), bounds=(0.0, 0.01), margin=0.02, sigmoid="long_tail")
+        g = self._gripper_caging_reward(action, obj, object_reach_radius=0.01, obj_radius=0.015, pad_success_thresh=0.02, xz_thresh=0.03,
+                                        desired_gripper_effort=0.1, high_density=True)
+        in_place = tolerance(o2t, bounds=(0, 0.02), margin=in_place_margin, sigmoid="long_tail")
+        reward = hamacher_product(g, in_place)
+        grasp_success = (tcp_to_obj < 0.04) and (obj[2] - 0.02 > self.obj_init_pos[2]) and not (obs[3] < 0.33)
+        if grasp_success:
+            reward += 1.0 + 5.0 * hamacher_product(in_place, above_floor)
+        if o2t < self.TARGET_RADIUS:
+            reward = 10.0
+        return reward, tcp_to_obj, grasp_success, o2t, g, in_place
+
+
 TASKS = {"reach-v3": Reach, "push-v3": Push, "pick-place-v3": PickPlace, "door-open-v3": DoorOpen,
          "drawer-open-v3": DrawerOpen, "drawer-close-v3": DrawerClose, "button-press-topdown-v3": ButtonPressTopdown,
-         "peg-insert-side-v3": PegInsertSide, "window-open-v3": WindowOpen, "window-close-v3": WindowClose}
+         "peg-insert-side-v3": PegInsertSide, "window-open-v3": WindowOpen, "window-close-v3": WindowClose,
+         "reach-wall-v3": ReachWall, "push-wall-v3": PushWall, "pick-place-wall-v3": PickPlaceWall, "push-back-v3": PushBack,
+         "sweep-v3": Sweep, "sweep-into-v3": SweepInto, "hand-insert-v3": HandInsert, "pick-out-of-hole-v3": PickOutOfHole}

@@ -106,6 +106,31 @@ def test_teacher_forced_one_step(torch_cuda, task):
     assert worst < TOL
 
 
+@pytest.mark.parametrize("task", _tasks_with_goldens())
+def test_teacher_forced_contact_rich(torch_cuda, task):
+    """Same, along trajectories driven by the reference's scripted policy (grasping / pushing / pressing contacts)."""
+    g = np.load(os.path.join(GOLD, f"traj_{task}.npz"))
+    if "p_actions" not in g:
+        pytest.skip("no policy trajectory in the fixture")
+    rig = Rig(torch_cuda, task, g["p_rand_vec"])
+    rig.reset()
+    nq, nv = g["p_qpos"].shape[2], g["p_qvel"].shape[2]
+    worst = 0.0
+    T = g["p_actions"].shape[1]
+    for t in range(0, T - 1, 3):
+        st = rig.eng.get_state()
+        for k in range(rig.n):
+            st[k]["qpos"][:nq] = g["p_qpos"][k, t]; st[k]["qvel"][:nv] = g["p_qvel"][k, t]
+            st[k]["mocap_pos"] = g["p_mocap"][k, t]; st[k]["prev_obs"] = g["p_obs"][k, t][:18]
+            st[k]["warm"][:] = 0; st[k]["path_len"] = t + 1
+        rig.eng.set_state(st)
+        o, r, info, _, _ = rig.step(g["p_actions"][:, t + 1])
+        eo = np.abs(o - g["p_obs"][:, t + 1]).max(); er = np.abs(r - g["p_reward"][:, t + 1]).max()
+        worst = max(worst, eo, er)
+    print(f"{task}: contact-rich teacher-forced worst err {worst:.2e}")
+    assert worst < 2e-3        # contacts: single-step error stays small; 1e-4 is met on the contact-free fixtures above
+
+
 def test_live_oracle_fresh_seed(torch_cuda):
     """Not a fixture: a goal and an action sequence the goldens never saw."""
     from oracle.tasks import TASKS as OT
