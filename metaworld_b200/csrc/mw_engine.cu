@@ -152,6 +152,7 @@ k_step(EngineDev e, const int* __restrict__ block_model, const int* __restrict__
   bool done = false;
   if (lane == 0) {
     ws->es.path_len += 1.f;
+    task_live_update(c);
     make_obs(c, ws->obs);
     real obsr[39]; for (int i = 0; i < 39; i++) obsr[i] = ws->obs[i];
     real rew, inf[INFO_N];

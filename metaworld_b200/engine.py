@@ -96,6 +96,10 @@ def task_const(spec: TaskSpec, lw: lower.Lowered) -> np.ndarray:
         tc["movable_pos0"] = m.arrays["body_pos"][m.names["body"].index(spec.movable)]
     p = np.zeros(16, dtype=np.float32)
     p[: len(spec.params)] = spec.params
+    if spec.site_params:
+        mm = modelzoo.full_model(spec.xml)
+        for k, nm in enumerate(spec.site_params):
+            p[3 * k: 3 * k + 3] = mm.arrays["site_pos"][mm.names["site"].index(nm)]
     # collider slots of the two finger pads (touching_object, sawyer_xyz_env.py:401-440)
     p[14] = lw.geom_names.index("leftpad_geom")
     p[15] = lw.geom_names.index("rightpad_geom")

