@@ -101,10 +101,24 @@ def _cpu_worker(args):
     return n, time.perf_counter() - t0
 
 
+def usable_cores():
+    """Host threads this process may actually use: the affinity mask capped by the cgroup CPU quota (the GPU boxes
+    show 128 logical cores but cpu.max = 16 CPUs)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def cpu_baseline(names, cores, steps_per_env, seed=42):
-    """Times the CPU restatement (oracle) of the same path: `cores` processes, each with its own sub-envs."""
+    """Times the CPU restatement (oracle) of the same path: `cores` processes, each with its own sub-envs; the task
+    types are dealt round-robin over the processes so every type of the workload is in the sample."""
     import multiprocessing as mp
-    per = max(1, min(len(names), 4))
+    per = max(1, -(-len(names) // cores))
     jobs = [([names[(c * per + k) % len(names)] for k in range(per)], steps_per_env, seed + 1000 * c) for c in range(cores)]
     t0 = time.perf_counter()
     if cores == 1:
@@ -125,7 +139,7 @@ def run_reference(args):
     from oracle import mjphys
     mjphys.build()
     names, _ = implemented_tasks(args.benchmark)
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     vals = []
     sample = ""
     t_all = time.perf_counter()
@@ -140,7 +154,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "env_steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * per_step_envs / value, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.benchmark} subset ({len(names)} task types) CPU restatement, random actions",
+            "config": {"workload": f"{args.benchmark}: {len(names)} task types, CPU restatement of the same step path, random actions U(-1,1)",
                        "tasks": names, "note": "reference CPU MuJoCo could not be executed (mujoco/gymnasium not installed, no network); timed: oracle/ float64 restatement"},
             "cpu_baseline": {"value": value, "unit": "env_steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "env_steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -259,8 +273,8 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=4096)
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--e2e-steps", type=int, default=50)
-    ap.add_argument("--cpu-steps-per-env", type=int, default=1500)
-    ap.add_argument("--ref-steps-per-env", type=int, default=400)
+    ap.add_argument("--cpu-steps-per-env", type=int, default=600)
+    ap.add_argument("--ref-steps-per-env", type=int, default=1000)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
