@@ -194,6 +194,7 @@ def run_ours(args):
     for i in range(W):
         env.step_torch(actions[i])
     torch.cuda.synchronize()
+    env.engine.profile()                            # clear the per-phase cycle counters
     if world > 1:
         dist.barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
@@ -207,6 +208,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     ms = sum(a.elapsed_time(b) for a, b in ev)
+    prof = env.engine.profile()
     # ---- e2e through the numpy API: pinned H2D of actions, D2H of obs/reward/flags/info inside the timed region
     Ke = max(3, min(K, args.e2e_steps))
     a_host = (np.random.default_rng(args.seed + rank).uniform(-1, 1, size=(Ke + 2, N, 4))).astype(np.float32)
@@ -256,6 +258,12 @@ def run_ours(args):
                              "note": "path is FP32-issue/latency bound (nv<=17, <1 KB state per env step); see DESIGN.md"},
                 "cpu_baseline": {"value": cpu_val, "unit": "env_steps/s", "cores": 1, "kind": "port", "sample": cpu_sample},
                 "clocks": sampler.summary(),
+                "phases": {"unit": "fraction of per-warp step cycles (clock64), timed region",
+                           **{k: round(prof[k] / max(1, prof["step"]), 4) for k in list(prof)[:8]},
+                           "warp_cycles_per_env_step": prof["step"] / max(1, N * K),
+                           "convex_pairs_per_env_step": prof["n_convex_pairs"] / max(1, N * K),
+                           "epa_expansions_per_env_step": prof["n_epa_expansions"] / max(1, N * K),
+                           "gjk_iters_per_env_step": prof["n_gjk_iters"] / max(1, N * K)},
                 "solver": {"mean_newton_iters_per_pass": counters["solver_iters"] / max(1, counters["forward_passes"]),
                            "contacts_dropped": counters["contacts_dropped"]}}
         print(json.dumps(line))

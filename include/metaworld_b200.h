@@ -45,6 +45,9 @@ int mw_set_envs(mw_engine*, int n_envs, const int* env_model);
  * distinct goal by the same device physics and cached.  Appends n snapshots, returns their ids.   */
 int mw_build_snapshots(mw_engine*, int n, const int* model_idx, const float* rand_vec /*[n,6]*/,
                        const unsigned char* partially_observable, int* snapshot_ids_out);
+/* Appends n snapshot records produced elsewhere (mw_get_snapshots of another engine, e.g. the float64 build of this
+ * library, or a checkpoint); same record layout, ids returned like mw_build_snapshots.                           */
+int mw_append_snapshots(mw_engine*, int n, const void* records, int* snapshot_ids_out);
 int mw_num_snapshots(const mw_engine*);
 /* copy snapshot records to the host (tests / checkpointing): out = n * mw_sizeof_snapshot() bytes */
 int mw_get_snapshots(mw_engine*, int first, int n, void* out);
@@ -86,6 +89,12 @@ int mw_debug_dump_floats(void);
 /* counters accumulated since the last call: [0] kernel launches, [1] env steps, [2] contacts dropped,
  * [3] solver iterations (sum over forward passes), [4] forward passes */
 int mw_get_counters(mw_engine*, unsigned long long* out5);
+
+/* per-phase SM cycle counters summed over all env steps since the last call (one warp = one env, so these are
+ * warp-cycles): [0] kinematics + mass matrix, [1] collision (incl. [2]), [2] GJK/EPA pairs, [3] constraint rows,
+ * [4] bias forces + unconstrained solve, [5] constraint solver, [6] integration + glue, [7] obs / reward / autoreset,
+ * [8] whole step; events: [9] GJK/EPA pair calls, [10] EPA expansions, [11] GJK iterations */
+int mw_get_profile(mw_engine*, unsigned long long* out12);
 
 #ifdef __cplusplus
 }

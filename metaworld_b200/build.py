@@ -63,8 +63,8 @@ def build(force=False, verbose=False, real_double=False, extra=()):
 
 
 def _build_f64(force=False, verbose=False):
-    if not force and os.path.exists(SO_F64) and os.path.getmtime(SO_F64) >= max(
-            os.path.getmtime(os.path.join(CSRC, f)) for f in SOURCES + HEADERS):
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS + ["mw_model.h", "mw_task_ids.h"]] + [os.path.join(_HERE, "..", "include", "metaworld_b200.h")]
+    if not force and os.path.exists(SO_F64) and os.path.getmtime(SO_F64) >= max(os.path.getmtime(d) for d in deps if os.path.exists(d)):
         return SO_F64
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-DMW_REAL_DOUBLE", "-DWARPS_PER_BLOCK=3", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -81,5 +81,10 @@ def _build_f64(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    build(force=True, verbose="-v" in sys.argv, real_double="--double" in sys.argv)
-    print(SO)
+    if "--double" in sys.argv:
+        print(build(force=True, verbose="-v" in sys.argv, real_double=True))
+    elif "--single" in sys.argv:
+        print(build(force=True, verbose="-v" in sys.argv))
+    else:   # both libraries: the float32 step engine and the float64 snapshot builder
+        print(build(force=True, verbose="-v" in sys.argv))
+        print(_build_f64(True, "-v" in sys.argv))

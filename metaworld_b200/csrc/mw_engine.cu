@@ -32,6 +32,8 @@ struct EngineDev {
   MwEnvState* state; MwSnapshot* snaps;
   const int* goal_first; const int* goal_count;      // device sampler ranges (may be NULL)
   int* diag;                                         // [n_envs][2]: contacts dropped, solver iterations
+  EpaWs* epa;                                        // GJK/EPA polytope workspace, one per launched warp (global memory)
+  unsigned long long* prof;                          // [12] summed cycle / event counters (mw_get_profile)
   int n_envs, max_steps, terminate_on_success; unsigned long long seed;
 };
 
@@ -96,7 +98,7 @@ DEV void store_env(WarpShared* ws, MwEnvState* dst, int lane) {
 }
 
 // observation assembly (sawyer_xyz_env.py:475-527 + clip :623-628); lane 0
-DEV void make_obs(const TaskCtx& c, float* obs) {
+DEV void make_obs(const TaskCtx& c, float* obs, bool clip = true) {   // reset() returns the observation unclipped (:664-682)
   real cur[18];
   mw_frame_pos(c.m, c.w, F_HAND, cur);
   real a[3], b[3]; mw_frame_pos(c.m, c.w, F_RCLAW, a); mw_frame_pos(c.m, c.w, F_LCLAW, b);
@@ -105,13 +107,13 @@ DEV void make_obs(const TaskCtx& c, float* obs) {
   const real hlo[3] = {(real)-0.525, (real)0.348, (real)-0.0525}, hhi[3] = {(real)0.525, (real)1.025, (real)0.7};
   for (int i = 0; i < 18; i++) {
     real v = cur[i], pv = c.s->prev_obs[i];
-    if (i < 3) { v = fmin(fmax(v, hlo[i]), hhi[i]); pv = fmin(fmax(pv, hlo[i]), hhi[i]); }
-    if (i == 3) { v = fmin(fmax(v, (real)-1), (real)1); pv = fmin(fmax(pv, (real)-1), (real)1); }
+    if (clip && i < 3) { v = fmin(fmax(v, hlo[i]), hhi[i]); pv = fmin(fmax(pv, hlo[i]), hhi[i]); }
+    if (clip && i == 3) { v = fmin(fmax(v, (real)-1), (real)1); pv = fmin(fmax(pv, (real)-1), (real)1); }
     obs[i] = (float)v; obs[18 + i] = (float)pv;
     c.s->prev_obs[i] = (float)cur[i];
   }
   for (int i = 0; i < 3; i++) {
-    real g = c.s->partially_observable != 0.f ? (real)0 : fmin(fmax((real)c.s->target[i], (real)c.tc->goal_lo[i]), (real)c.tc->goal_hi[i]);
+    real g = c.s->partially_observable != 0.f ? (real)0 : (clip ? fmin(fmax((real)c.s->target[i], (real)c.tc->goal_lo[i]), (real)c.tc->goal_hi[i]) : (real)c.s->target[i]);
     obs[36 + i] = (float)g;
   }
 }
@@ -135,9 +137,12 @@ k_step(EngineDev e, const int* __restrict__ block_model, const int* __restrict__
   if (warp >= block_count[blockIdx.x]) return;
   const int env = perm[block_start[blockIdx.x] + warp];
   WarpShared* ws = wsa + warp;
+  ws->w.epa = e.epa + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp);
   WarpScratch* w = &ws->w;
   const MwModel* m = (const MwModel*)bs->model;
   load_env(ws, e.state + env, lane);
+  if (lane < 12) w->prof[lane] = 0;
+  const long long t_begin = clock64();
   real act[4];
   for (int i = 0; i < 4; i++) act[i] = fmin(fmax((real)actions[4 * env + i], (real)-1), (real)1);
   TaskCtx c; c.m = m; c.tc = &bs->tc; c.w = w; c.s = &ws->es; c.action = act; c.meshvert = e.meshverts[mi];
@@ -150,6 +155,7 @@ k_step(EngineDev e, const int* __restrict__ block_model, const int* __restrict__
   mw_forward(m, c.meshvert, w, lane);
   iters += w->solver_iter; dropped += w->ncon_dropped;
   bool done = false;
+  const long long t_phys = clock64();
   if (lane == 0) {
     ws->es.path_len += 1.f;
     task_live_update(c);
@@ -166,8 +172,11 @@ k_step(EngineDev e, const int* __restrict__ block_model, const int* __restrict__
     reward[env] = (float)rew; terminated[env] = term; truncated[env] = trunc;
     ws->info[7] = (term || trunc) ? 1.f : 0.f;
     e.diag[2 * env] += dropped; e.diag[2 * env + 1] += iters;
+    w->prof[7] = clock64() - t_phys; w->prof[8] = clock64() - t_begin;
+    w->prof[6] = w->prof[8] - w->prof[7] - (w->prof[0] + w->prof[1] + w->prof[3] + w->prof[4] + w->prof[5]);   // euler + glue
   }
   SYNCW();
+  if (lane < 12 && e.prof) atomicAdd(e.prof + lane, (unsigned long long)w->prof[lane]);
   done = ws->info[7] != 0.f;
   if (lane < INFO_N) info_out[(size_t)env * INFO_N + lane] = ws->info[lane];
   if (!done) {
@@ -209,6 +218,7 @@ k_snapshot(EngineDev e, const int* __restrict__ block_model, const int* __restri
   if (warp >= block_count[blockIdx.x]) return;
   const int item = perm[block_start[blockIdx.x] + warp];
   WarpShared* ws = wsa + warp;
+  ws->w.epa = e.epa + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp);
   WarpScratch* w = &ws->w;
   const MwModel* m = (const MwModel*)bs->model;
   const float* rv = rand_vec + 6 * item;
@@ -241,7 +251,7 @@ k_snapshot(EngineDev e, const int* __restrict__ block_model, const int* __restri
   }
   if (lane == 0) {
     ws->es.partially_observable = partial[item] ? 1.f : 0.f;
-    make_obs(c, ws->obs);                              // _get_obs() of pass 2
+    make_obs(c, ws->obs, false);                       // _get_obs() of pass 2, not clipped
     for (int i = 0; i < 18; i++) { ws->obs[18 + i] = ws->obs[i]; }   // reset(): obs[18:36] = obs[:18]  (:679-680)
     ws->es.path_len = 0.f; ws->es.episode = 0.f; ws->es.ep_return = 0.f; ws->es.snapshot = (float)(snap_base + item);
   }
@@ -277,6 +287,7 @@ k_substeps(EngineDev e, const int* __restrict__ block_model, const int* __restri
   if (warp >= block_count[blockIdx.x]) return;
   const int env = perm[block_start[blockIdx.x] + warp];
   WarpShared* ws = wsa + warp;
+  ws->w.epa = e.epa + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp);
   const MwModel* m = (const MwModel*)bs->model;
   load_env(ws, e.state + env, lane);
   if (lane == 0) { ws->w.ctrl[0] = c0; ws->w.ctrl[1] = c1; }
@@ -307,13 +318,15 @@ struct mw_engine {
   std::vector<float*> meshbufs;
   MwEnvState* d_state = nullptr; MwSnapshot* d_snaps = nullptr; int snap_cap = 0, n_snaps = 0;
   int *d_goal_first = nullptr, *d_goal_count = nullptr, *d_diag = nullptr;
+  EpaWs* d_epa = nullptr; size_t epa_cap = 0;
+  unsigned long long* d_prof = nullptr;
   // env block table
   int n_blocks = 0; int *d_block_model = nullptr, *d_block_start = nullptr, *d_block_count = nullptr, *d_perm = nullptr;
   int max_steps = 500, terminate_on_success = 0; unsigned long long seed = 0;
   unsigned long long launches = 0, env_steps = 0;
   EngineDev dev() const {
     EngineDev e; e.models = d_models; e.model_stride = model_stride; e.taskconsts = d_tc; e.meshverts = d_meshptrs;
-    e.state = d_state; e.snaps = d_snaps; e.goal_first = d_goal_first; e.goal_count = d_goal_count; e.diag = d_diag;
+    e.state = d_state; e.snaps = d_snaps; e.goal_first = d_goal_first; e.goal_count = d_goal_count; e.diag = d_diag; e.epa = d_epa; e.prof = d_prof;
     e.n_envs = n_envs; e.max_steps = max_steps; e.terminate_on_success = terminate_on_success; e.seed = seed; return e;
   }
 };
@@ -327,6 +340,15 @@ static void make_blocks(int n_models, const std::vector<int>& item_model, std::v
     int cnt = (int)perm.size() - first;
     for (int o = 0; o < cnt; o += WARPS_PER_BLOCK) { bm.push_back(mi); bstart.push_back(first + o); bcount.push_back(cnt - o < WARPS_PER_BLOCK ? cnt - o : WARPS_PER_BLOCK); }
   }
+}
+static int ensure_epa(mw_engine* E, size_t n_blocks) {
+  size_t need = n_blocks * WARPS_PER_BLOCK;
+  if (need <= E->epa_cap) return 0;
+  if (E->d_epa) cudaFree(E->d_epa);
+  E->d_epa = nullptr; E->epa_cap = 0;
+  CK(cudaMalloc((void**)&E->d_epa, sizeof(EpaWs) * need));
+  E->epa_cap = need;
+  return 0;
 }
 template <class T> static int upload(T** dst, const std::vector<T>& v) {
   if (*dst) cudaFree(*dst);
@@ -375,6 +397,8 @@ int mw_create(mw_engine** out, int device, int n_models, const void* models, con
   }
   CK(cudaMalloc((void**)&E->d_meshptrs, sizeof(float*) * n_models));
   CK(cudaMemcpy(E->d_meshptrs, ptrs.data(), sizeof(float*) * n_models, cudaMemcpyHostToDevice));
+  CK(cudaMalloc((void**)&E->d_prof, sizeof(unsigned long long) * 12));
+  CK(cudaMemset(E->d_prof, 0, sizeof(unsigned long long) * 12));
   CK(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
   CK(cudaFuncSetAttribute(k_snapshot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
   CK(cudaFuncSetAttribute(k_substeps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
@@ -387,7 +411,7 @@ void mw_destroy(mw_engine* E) {
   cudaSetDevice(E->device);
   cudaFree(E->d_models); cudaFree(E->d_tc); cudaFree(E->d_meshptrs);
   for (float* p : E->meshbufs) cudaFree(p);
-  cudaFree(E->d_state); cudaFree(E->d_snaps); cudaFree(E->d_goal_first); cudaFree(E->d_goal_count); cudaFree(E->d_diag);
+  cudaFree(E->d_state); cudaFree(E->d_snaps); cudaFree(E->d_goal_first); cudaFree(E->d_goal_count); cudaFree(E->d_diag); cudaFree(E->d_epa); cudaFree(E->d_prof);
   cudaFree(E->d_block_model); cudaFree(E->d_block_start); cudaFree(E->d_block_count); cudaFree(E->d_perm);
   delete E;
 }
@@ -399,6 +423,7 @@ int mw_set_envs(mw_engine* E, int n_envs, const int* env_model) {
   for (int v : im) if (v < 0 || v >= E->n_models) return fail(MW_ERR_ARG, "mw_set_envs: model index out of range");
   make_blocks(E->n_models, im, bm, bs, bc, perm);
   E->n_envs = n_envs; E->n_blocks = (int)bm.size();
+  if (ensure_epa(E, bm.size())) return MW_ERR_CUDA;
   if (upload(&E->d_block_model, bm) || upload(&E->d_block_start, bs) || upload(&E->d_block_count, bc) || upload(&E->d_perm, perm)) return MW_ERR_CUDA;
   if (E->d_state) cudaFree(E->d_state);
   CK(cudaMalloc((void**)&E->d_state, sizeof(MwEnvState) * n_envs));
@@ -422,6 +447,7 @@ int mw_build_snapshots(mw_engine* E, int n, const int* model_idx, const float* r
   std::vector<int> im(model_idx, model_idx + n), bm, bs, bc, perm;
   for (int v : im) if (v < 0 || v >= E->n_models) return fail(MW_ERR_ARG, "mw_build_snapshots: model index out of range");
   make_blocks(E->n_models, im, bm, bs, bc, perm);
+  if (ensure_epa(E, bm.size())) return MW_ERR_CUDA;
   int *d_bm = nullptr, *d_bs = nullptr, *d_bc = nullptr, *d_perm = nullptr; float* d_rv = nullptr; unsigned char* d_po = nullptr;
   if (upload(&d_bm, bm) || upload(&d_bs, bs) || upload(&d_bc, bc) || upload(&d_perm, perm)) return MW_ERR_CUDA;
   CK(cudaMalloc((void**)&d_rv, sizeof(float) * 6 * n)); CK(cudaMemcpy(d_rv, rand_vec, sizeof(float) * 6 * n, cudaMemcpyHostToDevice));
@@ -432,6 +458,23 @@ int mw_build_snapshots(mw_engine* E, int n, const int* model_idx, const float* r
   cudaFree(d_bm); cudaFree(d_bs); cudaFree(d_bc); cudaFree(d_perm); cudaFree(d_rv); cudaFree(d_po);
   if (ids_out) for (int i = 0; i < n; i++) ids_out[i] = E->n_snaps + i;
   E->n_snaps += n; E->launches++;
+  return MW_OK;
+}
+int mw_append_snapshots(mw_engine* E, int n, const void* records, int* ids_out) {
+  if (!E || n <= 0 || !records) return fail(MW_ERR_ARG, "mw_append_snapshots: bad arguments");
+  CK(cudaSetDevice(E->device));
+  if (E->n_snaps + n > E->snap_cap) {
+    int cap = (E->n_snaps + n) * 2;
+    MwSnapshot* p = nullptr;
+    CK(cudaMalloc((void**)&p, sizeof(MwSnapshot) * cap));
+    if (E->n_snaps) CK(cudaMemcpy(p, E->d_snaps, sizeof(MwSnapshot) * E->n_snaps, cudaMemcpyDeviceToDevice));
+    cudaFree(E->d_snaps); E->d_snaps = p; E->snap_cap = cap;
+  }
+  std::vector<MwSnapshot> tmp((const MwSnapshot*)records, (const MwSnapshot*)records + n);
+  for (int i = 0; i < n; i++) tmp[i].st.snapshot = (float)(E->n_snaps + i);
+  CK(cudaMemcpy(E->d_snaps + E->n_snaps, tmp.data(), sizeof(MwSnapshot) * n, cudaMemcpyHostToDevice));
+  if (ids_out) for (int i = 0; i < n; i++) ids_out[i] = E->n_snaps + i;
+  E->n_snaps += n;
   return MW_OK;
 }
 int mw_num_snapshots(const mw_engine* E) { return E ? E->n_snaps : 0; }
@@ -514,6 +557,14 @@ int mw_get_counters(mw_engine* E, unsigned long long* out5) {
   for (int i = 0; i < E->n_envs; i++) { dropped += diag[2 * i]; iters += diag[2 * i + 1]; }
   out5[0] = E->launches; out5[1] = E->env_steps; out5[2] = dropped; out5[3] = iters; out5[4] = E->env_steps * 6ull;
   E->launches = 0; E->env_steps = 0;
+  return MW_OK;
+}
+
+int mw_get_profile(mw_engine* E, unsigned long long* out12) {
+  if (!E || !out12) return fail(MW_ERR_ARG, "mw_get_profile");
+  CK(cudaSetDevice(E->device));
+  CK(cudaMemcpy(out12, E->d_prof, sizeof(unsigned long long) * 12, cudaMemcpyDeviceToHost));
+  CK(cudaMemset(E->d_prof, 0, sizeof(unsigned long long) * 12));
   return MW_OK;
 }
 

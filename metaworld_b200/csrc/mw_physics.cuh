@@ -31,7 +31,7 @@ struct Contact {
 
 // region U is time-shared: (a) geom world poses + EPA workspace during collision, (b) efc_J afterwards
 #define MW_UWORDS_J (MW_MAXEFC * NVP)
-#define MW_UWORDS_C (MW_MAXGEOM * 12 + EPA_WS_WORDS)
+#define MW_UWORDS_C (MW_MAXGEOM * 12 * 2 + (int)(sizeof(EpaSm) / 4) + 2)   // geom world poses (creal) + EPA scratch during collision
 #define MW_UWORDS (MW_UWORDS_J > MW_UWORDS_C ? MW_UWORDS_J : MW_UWORDS_C)
 
 struct WarpScratch {
@@ -42,11 +42,13 @@ struct WarpScratch {
   real qfrc_smooth[MW_MAXDOF], qacc_smooth[MW_MAXDOF], qfrc_con[MW_MAXDOF], qacc[MW_MAXDOF];
   real vMa[MW_MAXDOF], vSearch[MW_MAXDOF], vMs[MW_MAXDOF], vTmp[MW_MAXDOF];
   real M[MW_MAXDOF * NVP], H[MW_MAXDOF * NVP];
-  real U[MW_UWORDS];
+  alignas(16) real U[MW_UWORDS];
+  EpaWs* epa;               // this warp's GJK/EPA polytope workspace (global memory, see mw_engine.cu)
   real eD[MW_MAXEFC], eAref[MW_MAXEFC], eJar[MW_MAXEFC], eJv[MW_MAXEFC], eF[MW_MAXEFC], eHd[MW_MAXEFC];
   Contact con[MW_MAXCON];
   unsigned short cand[64];
   int ncon, nefc, nscalar, nweld, solver_iter, ncon_dropped;
+  long long prof[12];       // cycle / event counters of this step (see MW_PROF_* in mw_engine.cu; lane 0 only)
 };
 
 #define SYNCW() __syncwarp()
@@ -302,18 +304,18 @@ __device__ __noinline__ real mw_rne_bias(const MwModel* __restrict__ m, WarpScra
 }
 
 // ------------------------------------------------------------------ collision  [MuJoCo mj_collision]
-DEV void mw_load_shape(const MwModel* m, const real* gpose, const float* meshvert, int g, DShape* s) {
+DEV void mw_load_shape(const MwModel* m, const creal* gpose, const float* meshvert, int g, DShape* s) {
   s->type = m->geom_type[g];
   for (int i = 0; i < 3; i++) { s->pos[i] = gpose[12 * g + i]; s->size[i] = m->geom_size[g][i]; }
   for (int i = 0; i < 9; i++) s->mat[i] = gpose[12 * g + 3 + i];
   s->vert = meshvert + 3 * m->geom_meshadr[g]; s->nvert = m->geom_meshnum[g];
 }
-DEV void make_frame(real* fr) {
+DEV void make_frame(creal* fr) {
   v3normalize(fr);
-  real* y = fr + 3; real* z = fr + 6;
+  creal* y = fr + 3; creal* z = fr + 6;
   v3zero(y);
-  if (fr[1] < (real)0.5 && fr[1] > (real)-0.5) y[1] = 1; else y[2] = 1;
-  real dp = v3dot(fr, y);
+  if (fr[1] < (creal)0.5 && fr[1] > (creal)-0.5) y[1] = 1; else y[2] = 1;
+  creal dp = v3dot(fr, y);
   v3addscl(y, y, fr, -dp);
   v3normalize(y);
   v3cross(z, fr, y);
@@ -322,9 +324,11 @@ DEV void mw_store_contact(const MwModel* m, WarpScratch* w, int slot, const RawC
   Contact* c = &w->con[slot];
   int prm = m->pair_param[pair];
   const float* P = m->param[prm];
-  c->dist = rc.dist;
-  for (int k = 0; k < 3; k++) { c->pos[k] = rc.pos[k]; c->frame[k] = rc.normal[k]; }
-  make_frame(c->frame);
+  c->dist = (real)rc.dist;
+  creal fr[9] = {rc.normal[0], rc.normal[1], rc.normal[2], 0, 0, 0, 0, 0, 0};
+  make_frame(fr);
+  for (int k = 0; k < 3; k++) c->pos[k] = (real)rc.pos[k];
+  for (int k = 0; k < 9; k++) c->frame[k] = (real)fr[k];
   c->g1 = m->pair_g1[pair]; c->g2 = m->pair_g2[pair];
   c->incl = P[1]; c->dim = (int)P[2]; c->fr1 = P[3]; c->fr3 = P[4]; c->mu = P[3];
   c->solref[0] = P[5]; c->solref[1] = P[6];
@@ -333,15 +337,25 @@ DEV void mw_store_contact(const MwModel* m, WarpScratch* w, int slot, const RawC
 }
 
 __device__ __noinline__ void mw_collide(const MwModel* __restrict__ m, const float* __restrict__ meshvert, WarpScratch* w, int lane) {
-  real* gpose = w->U;                                   // [ngeom][12]
-  EpaWs* epa = (EpaWs*)(w->U + MW_MAXGEOM * 12);
+  creal* gpose = (creal*)w->U;                          // [ngeom][12] world poses, float64 from here on
+  EpaWs* epa = w->epa;
+  EpaSm* esm = (EpaSm*)(gpose + MW_MAXGEOM * 12);
   const int ng = m->ngeom, np = m->npair;
   for (int g = lane; g < ng; g += 32) {
-    int l = m->geom_link[g];
-    real pos[3]; mw_attach(w, l, m->geom_shift[g], m->geom_pos[g], pos);
-    real Rl[9]; for (int i = 0; i < 9; i++) Rl[i] = m->geom_mat[g][i];
-    real Rw[9];
-    if (l < 0) { for (int i = 0; i < 9; i++) Rw[i] = Rl[i]; } else mat_mul(Rw, w->lmat[l], Rl);
+    const int l = m->geom_link[g];
+    creal gp[3] = {m->geom_pos[g][0], m->geom_pos[g][1], m->geom_pos[g][2]}, pos[3];
+    creal Rl[9]; for (int i = 0; i < 9; i++) Rl[i] = m->geom_mat[g][i];
+    creal Rw[9];
+    if (l < 0) {
+      for (int i = 0; i < 3; i++) pos[i] = gp[i] + (m->geom_shift[g] ? (creal)w->shift[i] : (creal)0);
+      for (int i = 0; i < 9; i++) Rw[i] = Rl[i];
+    } else {
+      creal Lm[9], Lp[3], t[3];
+      for (int i = 0; i < 9; i++) Lm[i] = w->lmat[l][i];
+      for (int i = 0; i < 3; i++) Lp[i] = w->lpos[l][i];
+      mat_mulvec(t, Lm, gp); v3add(pos, Lp, t);
+      mat_mul(Rw, Lm, Rl);
+    }
     for (int i = 0; i < 3; i++) gpose[12 * g + i] = pos[i];
     for (int i = 0; i < 9; i++) gpose[12 * g + 3 + i] = Rw[i];
   }
@@ -351,29 +365,29 @@ __device__ __noinline__ void mw_collide(const MwModel* __restrict__ m, const flo
   for (int base = 0; base < np; base += 32) {
     int p = base + lane;
     // ---- broadphase cull (conservative: never removes a pair that is within margin)
-    bool keep = false; int g1 = 0, g2 = 0; real margin = 0;
+    bool keep = false; int g1 = 0, g2 = 0; creal margin = 0;
     if (p < np) {
       g1 = m->pair_g1[p]; g2 = m->pair_g2[p];
       margin = m->param[m->pair_param[p]][0];
       int t1 = m->geom_type[g1], t2 = m->geom_type[g2];
-      const real* p1 = gpose + 12 * g1; const real* p2 = gpose + 12 * g2;
-      real r1 = m->geom_rbound[g1], r2 = m->geom_rbound[g2];
+      const creal* p1 = gpose + 12 * g1; const creal* p2 = gpose + 12 * g2;
+      creal r1 = m->geom_rbound[g1], r2 = m->geom_rbound[g2];
       if (t1 == G_PLANE) {
-        real n[3], t[3]; mat_col(n, p1 + 3, 2); v3sub(t, p2, p1);
+        creal n[3], t[3]; mat_col(n, p1 + 3, 2); v3sub(t, p2, p1);
         keep = v3dot(t, n) <= r2 + margin;
       } else {
-        real t[3]; v3sub(t, p2, p1);
-        real bound = r1 + r2 + margin;
+        creal t[3]; v3sub(t, p2, p1);
+        creal bound = r1 + r2 + margin;
         keep = v3dot(t, t) <= bound * bound;
         if (keep && t2 == G_BOX) {   // bounding sphere of g1 against the exact box g2
-          real cl[3], dd = 0; mat_tmulvec(cl, p2 + 3, t); // centre of g1 in box-2 frame is -R2^T t
-          for (int i = 0; i < 3; i++) { real e = fabs(cl[i]) - m->geom_size[g2][i]; if (e > 0) dd += e * e; }
-          real b = r1 + margin; keep = dd <= b * b;
+          creal cl[3], dd = 0; mat_tmulvec(cl, p2 + 3, t); // centre of g1 in box-2 frame is -R2^T t
+          for (int i = 0; i < 3; i++) { creal e = fabs(cl[i]) - m->geom_size[g2][i]; if (e > 0) dd += e * e; }
+          creal b = r1 + margin; keep = dd <= b * b;
         }
         if (keep && t1 == G_BOX) {
-          real cl[3], dd = 0; mat_tmulvec(cl, p1 + 3, t);
-          for (int i = 0; i < 3; i++) { real e = fabs(cl[i]) - m->geom_size[g1][i]; if (e > 0) dd += e * e; }
-          real b = r2 + margin; keep = dd <= b * b;
+          creal cl[3], dd = 0; mat_tmulvec(cl, p1 + 3, t);
+          for (int i = 0; i < 3; i++) { creal e = fabs(cl[i]) - m->geom_size[g1][i]; if (e > 0) dd += e * e; }
+          creal b = r2 + margin; keep = dd <= b * b;
         }
       }
     }
@@ -383,6 +397,11 @@ __device__ __noinline__ void mw_collide(const MwModel* __restrict__ m, const flo
     if (analytic) {
       DShape a, b; mw_load_shape(m, gpose, meshvert, g1, &a); mw_load_shape(m, gpose, meshvert, g2, &b);
       cnt = narrow_analytic(a, b, margin, rc);
+    } else if (keep && m->geom_type[g1] == G_CYLINDER && (m->geom_type[g2] == G_BOX || m->geom_type[g2] == G_CYLINDER)) {
+      // axis-aligned cylinder-box / parallel cylinders: exact, one pair per lane; anything else falls through to GJK/EPA
+      DShape a, b; mw_load_shape(m, gpose, meshvert, g1, &a); mw_load_shape(m, gpose, meshvert, g2, &b);
+      const int r = b.type == G_BOX ? cyl_box_aligned(a, b, margin, rc) : cyl_cyl_parallel(a, b, margin, rc);
+      if (r >= 0) { cnt = r; analytic = true; }
     }
     // deterministic compaction: exclusive prefix of counts over lanes
     int incl = cnt;
@@ -398,15 +417,15 @@ __device__ __noinline__ void mw_collide(const MwModel* __restrict__ m, const flo
       int pp = base + src;
       int h1 = m->pair_g1[pp], h2 = m->pair_g2[pp];
       DShape a, b; mw_load_shape(m, gpose, meshvert, h1, &a); mw_load_shape(m, gpose, meshvert, h2, &b);
-      real mg = m->param[m->pair_param[pp]][0];
+      creal mg = m->param[m->pair_param[pp]][0];
       RawCon r1; int c1;
       if (a.type == G_PLANE) {   // plane - mesh: support vertex against the plane
-        real n[3], nd[3], sp[3], t[3]; mat_col(n, a.mat, 2); v3scl(nd, n, -1);
+        creal n[3], nd[3], sp[3], t[3]; mat_col(n, a.mat, 2); v3scl(nd, n, -1);
         support_shape(b, nd, sp, lane);
         v3sub(t, sp, a.pos);
-        r1.dist = v3dot(t, n); v3copy(r1.normal, n); v3addscl(r1.pos, sp, n, -(real)0.5 * r1.dist);
+        r1.dist = v3dot(t, n); v3copy(r1.normal, n); v3addscl(r1.pos, sp, n, -(creal)0.5 * r1.dist);
         c1 = r1.dist <= mg;
-      } else c1 = convex_pair(a, b, mg, &r1, epa, lane);
+      } else { long long tc = clock64(); c1 = convex_pair(a, b, mg, &r1, esm, epa, lane, w->prof); if (lane == 0) { w->prof[2] += clock64() - tc; w->prof[9] += 1; } }
       if (c1) { if (ncon < MW_MAXCON && lane == 0) mw_store_contact(m, w, ncon, r1, pp); ncon++; }
     }
   }
@@ -779,11 +798,16 @@ __device__ __noinline__ void mw_solve(const MwModel* __restrict__ m, WarpScratch
 // mj_forward  (positions -> qacc); leaves link poses / contacts / efc forces in the scratch.
 __device__ __noinline__ void mw_forward(const MwModel* __restrict__ m, const float* __restrict__ meshvert, WarpScratch* w, int lane) {
   const int nv = m->nv;
+  long long t0 = clock64(), t1;
+#define PROF_(i) { t1 = clock64(); if (lane == 0) w->prof[i] += t1 - t0; t0 = t1; }
   mw_kinematics(m, w, lane);
   LaneDof L; mw_lane_dof(m, w, lane, &L);
   mw_mass_matrix(m, w, L, lane);
+  PROF_(0)
   mw_collide(m, meshvert, w, lane);
+  PROF_(1)
   mw_make_constraints(m, w, L, lane);
+  PROF_(3)
   real bias = mw_rne_bias(m, w, L, lane);
   // passive + actuation  [mj_passive, mj_fwdActuation]
   real qfs = 0;
@@ -805,7 +829,10 @@ __device__ __noinline__ void mw_forward(const MwModel* __restrict__ m, const flo
   real as = mw_chol_solve(w->H, qfs, nv, lane);
   if (lane < nv) w->qacc_smooth[lane] = as;
   SYNCW();
+  PROF_(4)
   mw_solve(m, w, lane, sizeof(real) == 4 ? 8 : 50);
+  PROF_(5)
+#undef PROF_
 }
 
 // mj_Euler: semi-implicit, joint damping implicit

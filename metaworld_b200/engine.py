@@ -15,8 +15,10 @@ from . import lower, modelzoo
 from .tasks import TASKS, TaskSpec
 
 _LIB = None
+_LIB64 = None
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("MW_B200_LIB") or os.path.join(_HERE, "libmwb200.so")   # MW_B200_LIB=.../libmwb200_f64.so selects the double build
+SO64_PATH = os.path.join(_HERE, "libmwb200_f64.so")   # same kernels with real=double: builds the episode-start snapshots
 
 TASKCONST_DTYPE = np.dtype([("task_id", "i4"), ("nframe_task", "i4"), ("main_geom", "i4"), ("pad", "i4"),
                             ("hand_init", "f4", 3), ("mocap_lo", "f4", 3), ("mocap_hi", "f4", 3),
@@ -35,42 +37,57 @@ class EngineError(RuntimeError):
     pass
 
 
+def _load(path):
+    if not os.path.exists(path):
+        raise EngineError(f"{path} is missing: build it with `python -m metaworld_b200.build` (and `--double`); "
+                          "the engine has no CPU fallback")
+    L = C.CDLL(path)
+    L.mw_last_error.restype = C.c_char_p
+    L.mw_build_info.restype = C.c_char_p
+    vp, ip = C.c_void_p, C.c_int
+    L.mw_create.argtypes = [C.POINTER(vp), ip, ip, vp, vp, C.POINTER(vp), vp]
+    L.mw_destroy.argtypes = [vp]
+    L.mw_set_envs.argtypes = [vp, ip, vp]
+    L.mw_build_snapshots.argtypes = [vp, ip, vp, vp, vp, vp]
+    L.mw_append_snapshots.argtypes = [vp, ip, vp, vp]
+    L.mw_num_snapshots.argtypes = [vp]
+    L.mw_get_snapshots.argtypes = [vp, ip, ip, vp]
+    L.mw_reset.argtypes = [vp, ip, vp, vp, vp, ip, vp]
+    L.mw_step.argtypes = [vp, vp, vp, ip, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.mw_set_options.argtypes = [vp, ip, ip, C.c_ulonglong]
+    L.mw_set_goal_sets.argtypes = [vp, vp, vp]
+    L.mw_get_state.argtypes = [vp, vp]
+    L.mw_set_state.argtypes = [vp, vp]
+    L.mw_debug_substeps.argtypes = [vp, ip, vp, vp]
+    L.mw_get_counters.argtypes = [vp, vp]
+    L.mw_debug_forward.argtypes = [vp, vp, vp, vp]
+    L.mw_get_profile.argtypes = [vp, vp]
+    assert L.mw_sizeof_model() == lower.DTYPE.itemsize, "MwModel layout mismatch (rebuild the library)"
+    assert L.mw_sizeof_taskconst() == TASKCONST_DTYPE.itemsize
+    assert L.mw_sizeof_envstate() == ENVSTATE_DTYPE.itemsize == 512
+    assert L.mw_sizeof_snapshot() == SNAPSHOT_DTYPE.itemsize == 768
+    return L
+
+
 def lib():
     global _LIB
     if _LIB is None:
-        if not os.path.exists(SO_PATH):
-            raise EngineError(f"{SO_PATH} is missing: build it with `python -m metaworld_b200.build` "
-                              "(the engine has no CPU fallback)")
-        L = C.CDLL(SO_PATH)
-        L.mw_last_error.restype = C.c_char_p
-        L.mw_build_info.restype = C.c_char_p
-        vp, ip = C.c_void_p, C.c_int
-        L.mw_create.argtypes = [C.POINTER(vp), ip, ip, vp, vp, C.POINTER(vp), vp]
-        L.mw_destroy.argtypes = [vp]
-        L.mw_set_envs.argtypes = [vp, ip, vp]
-        L.mw_build_snapshots.argtypes = [vp, ip, vp, vp, vp, vp]
-        L.mw_num_snapshots.argtypes = [vp]
-        L.mw_get_snapshots.argtypes = [vp, ip, ip, vp]
-        L.mw_reset.argtypes = [vp, ip, vp, vp, vp, ip, vp]
-        L.mw_step.argtypes = [vp, vp, vp, ip, vp, vp, vp, vp, vp, vp, vp, vp]
-        L.mw_set_options.argtypes = [vp, ip, ip, C.c_ulonglong]
-        L.mw_set_goal_sets.argtypes = [vp, vp, vp]
-        L.mw_get_state.argtypes = [vp, vp]
-        L.mw_set_state.argtypes = [vp, vp]
-        L.mw_debug_substeps.argtypes = [vp, ip, vp, vp]
-        L.mw_get_counters.argtypes = [vp, vp]
-        L.mw_debug_forward.argtypes = [vp, vp, vp, vp]
-        assert L.mw_sizeof_model() == lower.DTYPE.itemsize, "MwModel layout mismatch (rebuild the library)"
-        assert L.mw_sizeof_taskconst() == TASKCONST_DTYPE.itemsize
-        assert L.mw_sizeof_envstate() == ENVSTATE_DTYPE.itemsize == 512
-        assert L.mw_sizeof_snapshot() == SNAPSHOT_DTYPE.itemsize == 768
-        _LIB = L
+        _LIB = _load(SO_PATH)
     return _LIB
 
 
-def _ck(rc):
+def lib64():
+    """The float64 build of the same CUDA kernels.  Episode-start snapshots (the reference's 2 x 250-substep reset) are
+    computed with it once per goal, so that contact-rich resting configurations start from the float64 answer."""
+    global _LIB64
+    if _LIB64 is None:
+        _LIB64 = _load(SO64_PATH)
+    return _LIB64
+
+
+def _ck(rc, L=None):
     if rc != 0:
-        raise EngineError(lib().mw_last_error().decode() or f"libmwb200 error {rc}")
+        raise EngineError((L or lib()).mw_last_error().decode() or f"libmwb200 error {rc}")
 
 
 _LOWERED: dict = {}
@@ -125,11 +142,16 @@ class Engine:
         ptrs = (C.c_void_p * len(self._mesh))(*[m.ctypes.data if len(m) else None for m in self._mesh])
         nmv = np.array([len(m) for m in self._mesh], dtype=np.int32)
         self.h = C.c_void_p()
+        self._create_args = (device, len(self.specs), models, tcs, ptrs, nmv)
         _ck(lib().mw_create(C.byref(self.h), device, len(self.specs), models.ctypes.data, tcs.ctypes.data, ptrs,
                             nmv.ctypes.data))
+        self.h64 = None
         self.n_envs = 0
 
     def close(self):
+        if getattr(self, "h64", None):
+            lib64().mw_destroy(self.h64)
+            self.h64 = None
         if getattr(self, "h", None):
             lib().mw_destroy(self.h)
             self.h = None
@@ -149,14 +171,30 @@ class Engine:
     def set_options(self, max_episode_steps=500, terminate_on_success=False, seed=0):
         _ck(lib().mw_set_options(self.h, int(max_episode_steps), int(bool(terminate_on_success)), int(seed) & (2**64 - 1)))
 
-    def build_snapshots(self, model_idx, rand_vec, partially_observable):
+    def build_snapshots(self, model_idx, rand_vec, partially_observable, precise=None):
+        """Episode-start snapshots for (model slot, rand_vec) pairs.  `precise` (default: on unless
+        MW_B200_SNAPSHOT_F32=1) runs the reset on the float64 build of the kernels and uploads the records."""
         mi = np.ascontiguousarray(model_idx, dtype=np.int32)
         rv = np.zeros((len(mi), 6), dtype=np.float32)
         rand_vec = np.asarray(rand_vec, dtype=np.float64).reshape(len(mi), -1)
         rv[:, : rand_vec.shape[1]] = rand_vec
         po = np.ascontiguousarray(partially_observable, dtype=np.uint8)
         ids = np.zeros(len(mi), dtype=np.int32)
-        _ck(lib().mw_build_snapshots(self.h, len(mi), mi.ctypes.data, rv.ctypes.data, po.ctypes.data, ids.ctypes.data))
+        if precise is None:
+            precise = os.environ.get("MW_B200_SNAPSHOT_F32", "0") != "1" and SO_PATH != SO64_PATH
+        if not precise:
+            _ck(lib().mw_build_snapshots(self.h, len(mi), mi.ctypes.data, rv.ctypes.data, po.ctypes.data, ids.ctypes.data))
+            return ids
+        L = lib64()
+        if self.h64 is None:
+            device, nm, models, tcs, ptrs, nmv = self._create_args
+            self.h64 = C.c_void_p()
+            _ck(L.mw_create(C.byref(self.h64), device, nm, models.ctypes.data, tcs.ctypes.data, ptrs, nmv.ctypes.data), L)
+        first = L.mw_num_snapshots(self.h64)
+        _ck(L.mw_build_snapshots(self.h64, len(mi), mi.ctypes.data, rv.ctypes.data, po.ctypes.data, None), L)
+        rec = np.zeros(len(mi), dtype=SNAPSHOT_DTYPE)
+        _ck(L.mw_get_snapshots(self.h64, first, len(mi), rec.ctypes.data), L)
+        _ck(lib().mw_append_snapshots(self.h, len(mi), rec.ctypes.data, ids.ctypes.data))
         return ids
 
     def get_snapshots(self, first=0, n=None):
@@ -211,6 +249,16 @@ class Engine:
         a = buf.cpu().numpy()
         ncw = (nf - 17 - 4)
         return a[:, :ncw].reshape(self.n_envs, -1, 12), a[:, ncw:ncw + 17], a[:, ncw + 17:]
+
+    PROFILE_KEYS = ["kin_mass", "collide", "gjk_epa", "constraints", "bias_smooth", "solver", "euler_glue", "obs_reward", "step",
+                    "n_convex_pairs", "n_epa_expansions", "n_gjk_iters"]
+
+    def profile(self):
+        """Per-phase warp-cycle counters summed over all env steps since the last call (mw_get_profile)."""
+        out = np.zeros(12, dtype=np.uint64)
+        self.torch.cuda.synchronize(self.device)
+        _ck(lib().mw_get_profile(self.h, out.ctypes.data))
+        return dict(zip(self.PROFILE_KEYS, (int(x) for x in out)))
 
     def counters(self):
         out = np.zeros(5, dtype=np.uint64)

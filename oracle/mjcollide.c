@@ -216,6 +216,7 @@ static double seg_box_min(const double* p0, const double* dir, const double* siz
     double f0 = A * t0 * t0 + B * t0 + C, f1 = A * t1 * t1 + B * t1 + C;
     double ts = A > 0 ? -B / (2 * A) : t0; if (ts < t0) ts = t0; if (ts > t1) ts = t1;
     f = A * ts * ts + B * ts + C;
+    if (f0 < 0) f0 = 0; if (f1 < 0) f1 = 0; if (f < 0) f = 0;   /* a squared distance: clear negative round-off */
     if (fmax(f0, f1) - f <= 1e-9 * f + 1e-18) { tl = t0; th = t1; f = fmin(f0, f1) < f ? fmin(f0, f1) : f; } /* flat: segment parallel to the face */
     else { tl = th = ts; }
     if (f < best - (1e-9 * best + 1e-18)) { best = f; blo = tl; bhi = th; }
@@ -232,9 +233,35 @@ static int capsule_box(const Shape* a, const Shape* b, double margin, RawCon* o)
   v3sub(t, p1, b->pos); mat_tmulvec(l1, b->mat, t);
   v3sub(dir, l1, l0);
   double tlo, thi;
-  seg_box_min(l0, dir, b->size, &tlo, &thi);
+  double best = seg_box_min(l0, dir, b->size, &tlo, &thi);
   int cnt = 0;
   double c[3];
+  if (best <= 1e-18) {
+    /* The capsule axis passes through the box: the distance is zero along [tlo, thi] and the witness direction is
+       undefined.  Rule (same on the device): the box face of minimum depth at the midpoint of that interval is the
+       contact face for both interval ends; depth is measured at each end. */
+    double cm[3], tm = 0.5 * (tlo + thi);
+    for (int i = 0; i < 3; i++) cm[i] = l0[i] + tm * dir[i];
+    int k = 0; double bd = 1e300, sgn = 1;
+    for (int i = 0; i < 3; i++) {
+      double dpos = b->size[i] - cm[i], dneg = b->size[i] + cm[i];
+      if (dpos < bd) { bd = dpos; k = i; sgn = 1; }
+      if (dneg < bd) { bd = dneg; k = i; sgn = -1; }
+    }
+    int nend = thi - tlo > 1e-9 ? 2 : 1;
+    for (int e = 0; e < nend; e++) {
+      double te = e ? thi : tlo, ce[3], nl[3] = {0, 0, 0}, pl[3];
+      for (int i = 0; i < 3; i++) ce[i] = l0[i] + te * dir[i];
+      double depth = b->size[k] - sgn * ce[k]; if (depth < 0) depth = 0;
+      nl[k] = -sgn;
+      v3copy(pl, ce); pl[k] = ce[k] + sgn * 0.5 * (depth - a->size[0]);
+      RawCon* r = o + cnt++;
+      r->dist = -(depth + a->size[0]);
+      mat_mulvec(r->normal, b->mat, nl);
+      mat_mulvec(r->pos, b->mat, pl); v3add(r->pos, r->pos, b->pos);
+    }
+    return cnt;
+  }
   if (thi - tlo > 1e-9) {
     v3addscl(c, p0, ax, 2 * a->size[1] * tlo); cnt += sphere_box_raw(c, a->size[0], b, margin, o + cnt);
     v3addscl(c, p0, ax, 2 * a->size[1] * thi); cnt += sphere_box_raw(c, a->size[0], b, margin, o + cnt);
@@ -473,8 +500,10 @@ static void simplex_weights(const SV* s, int n, double* w) {
   closest_tri(s[0].v, s[1].v, s[2].v, w);
 }
 
-#define EPA_MAXV 160
+#define EPA_MAXV 64
 #define EPA_MAXF 320
+#define EPA_ITERS 50
+#define EPA_TOL 1e-6
 typedef struct { int v[3]; double n[3], d; int alive; } EFace;
 
 static int epa_add_face(EFace* F, int* nf, const SV* V, int a, int b, int c) {
@@ -524,33 +553,35 @@ static int epa(const Shape* A, const Shape* B, SV* s, int n, RawCon* o, double* 
   for (int i = 0; i < 4; i++) V[nv++] = s[i];
   epa_add_face(F, &nf, V, 0, 1, 2); epa_add_face(F, &nf, V, 0, 2, 3); epa_add_face(F, &nf, V, 0, 3, 1); epa_add_face(F, &nf, V, 1, 3, 2);
   int bestf = -1;
-  for (int it = 0; it < 176; it++) {
+  /* expansion loop; iteration limit and tolerance follow MuJoCo's mjOption defaults for its convex collision pipeline
+     (ccd_iterations = 50, ccd_tolerance = 1e-6) [3P] */
+  for (int it = 0; it < EPA_ITERS; it++) {
     bestf = -1; double bd = 1e300;
     for (int f = 0; f < nf; f++) if (F[f].alive && F[f].d < bd) { bd = F[f].d; bestf = f; }
     if (bestf < 0) return 0;
     SV w; support(A, B, F[bestf].n, &w);
     double dw = v3dot(w.v, F[bestf].n);
-    if (dw - bd < 1e-10 || nv >= EPA_MAXV) break;
-    /* remove faces visible from w, collect horizon */
-    int edges[EPA_MAXF * 3][2]; int ne = 0;
+    if (dw - bd < EPA_TOL || nv >= EPA_MAXV) break;
+    /* faces visible from w, in index order */
+    int vis[EPA_MAXF], nvis = 0;
     for (int f = 0; f < nf; f++) {
       if (!F[f].alive) continue;
       double t[3]; v3sub(t, w.v, V[F[f].v[0]].v);
-      if (v3dot(F[f].n, t) > 1e-14) {
-        F[f].alive = 0;
-        for (int e = 0; e < 3; e++) {
-          int ea = F[f].v[e], eb = F[f].v[(e + 1) % 3], found = -1;
-          for (int q = 0; q < ne; q++) if (edges[q][0] == eb && edges[q][1] == ea) { found = q; break; }
-          if (found >= 0) { edges[found][0] = edges[ne - 1][0]; edges[found][1] = edges[ne - 1][1]; ne--; }
-          else { edges[ne][0] = ea; edges[ne][1] = eb; ne++; }
-        }
-      }
+      if (v3dot(F[f].n, t) > 1e-14) vis[nvis++] = f;
     }
-    if (ne == 0) break;
+    /* horizon = edges of visible faces whose reverse is not an edge of a visible face; order: (face, edge) ascending */
+    int edges[EPA_MAXF * 3][2]; int ne = 0;
+    for (int x = 0; x < nvis; x++)
+      for (int e = 0; e < 3; e++) {
+        int ea = F[vis[x]].v[e], eb = F[vis[x]].v[(e + 1) % 3], shared = 0;
+        for (int y = 0; y < nvis && !shared; y++)
+          for (int e2 = 0; e2 < 3; e2++) if (F[vis[y]].v[e2] == eb && F[vis[y]].v[(e2 + 1) % 3] == ea) { shared = 1; break; }
+        if (!shared) { edges[ne][0] = ea; edges[ne][1] = eb; ne++; }
+      }
+    for (int x = 0; x < nvis; x++) F[vis[x]].alive = 0;
+    if (ne == 0 || nf + ne > EPA_MAXF) break;
     int wi = nv; V[nv++] = w;
-    int fail = 0;
-    for (int q = 0; q < ne; q++) if (epa_add_face(F, &nf, V, edges[q][0], edges[q][1], wi) != 0) { fail = 1; break; }
-    if (fail) break;
+    for (int q = 0; q < ne; q++) epa_add_face(F, &nf, V, edges[q][0], edges[q][1], wi);
   }
   if (bestf < 0) return 0;
   /* witness points from the closest face */
@@ -635,7 +666,88 @@ static void refine_cyl_box(const Shape* A, const Shape* B, RawCon* o) {
   mat_mulvec(o->pos, B->mat, P); v3add(o->pos, o->pos, B->pos);
 }
 
+/* Cylinder vs box with the cylinder axis parallel to a box axis (buttons in housings, handles, a puck at rest): the
+   problem separates into an interval overlap along the axis and disc-vs-rectangle in the plane across it, so distance,
+   penetration depth and normal are exact and cheap.  Returns -1 when the axes are not parallel (GJK/EPA handles it). */
+static int cyl_box_aligned(const Shape* A, const Shape* B, double margin, RawCon* o) {
+  double ax[3], a[3], t[3], c[3];
+  mat_col(ax, A->mat, 2); mat_tmulvec(a, B->mat, ax);
+  int k = 0; for (int q = 1; q < 3; q++) if (fabs(a[q]) > fabs(a[k])) k = q;
+  if (fabs(a[k]) < 1 - 1e-6) return -1;      /* within ~1.4 mrad: MJCF quaternions like "0.7074 0.7068 0 0" are "parallel" */
+  const int i = (k + 1) % 3, j = (k + 2) % 3;
+  v3sub(t, A->pos, B->pos); mat_tmulvec(c, B->mat, t);
+  const double r = A->size[0], h = A->size[1]; const double* s = B->size;
+  const double cz = c[k], sz = cz >= 0 ? 1 : -1;
+  const double ga = fabs(cz) - (h + s[k]);                       /* axial gap (negative: overlap) */
+  const double p[2] = {c[i], c[j]};
+  const double q[2] = {fmin(fmax(p[0], -s[i]), s[i]), fmin(fmax(p[1], -s[j]), s[j])};
+  double n2[2], gr;                                              /* in-plane direction box -> cylinder, radial gap */
+  if (q[0] != p[0] || q[1] != p[1]) {
+    const double dv[2] = {p[0] - q[0], p[1] - q[1]}, dl = sqrt(dv[0] * dv[0] + dv[1] * dv[1]);
+    gr = dl - r; n2[0] = dv[0] / dl; n2[1] = dv[1] / dl;
+  } else {
+    const double ei = s[i] - fabs(p[0]), ej = s[j] - fabs(p[1]);
+    if (ei <= ej) { gr = -ei - r; n2[0] = p[0] >= 0 ? 1 : -1; n2[1] = 0; }
+    else { gr = -ej - r; n2[0] = 0; n2[1] = p[1] >= 0 ? 1 : -1; }
+  }
+  double nB[3] = {0, 0, 0}, P[3], dist;
+  if (ga > 0 && gr > 0) {                                        /* rim against a box edge */
+    dist = sqrt(ga * ga + gr * gr);
+    nB[i] = gr * n2[0] / dist; nB[j] = gr * n2[1] / dist; nB[k] = ga * sz / dist;
+    P[i] = 0.5 * (p[0] - r * n2[0] + q[0]); P[j] = 0.5 * (p[1] - r * n2[1] + q[1]); P[k] = 0.5 * (cz - sz * h + sz * s[k]);
+  } else if (ga > gr) {                                          /* cap against a box face */
+    dist = ga; nB[k] = sz;
+    P[i] = q[0]; P[j] = q[1]; P[k] = sz * s[k] + 0.5 * ga * sz;
+  } else {                                                       /* side against a box face or edge */
+    dist = gr; nB[i] = n2[0]; nB[j] = n2[1];
+    const double z0 = fmax(cz - h, -s[k]), z1 = fmin(cz + h, s[k]);
+    P[i] = p[0] - (r + 0.5 * gr) * n2[0]; P[j] = p[1] - (r + 0.5 * gr) * n2[1]; P[k] = 0.5 * (z0 + z1);
+  }
+  if (dist > margin + 1e-4) return 0;                            /* slack: the refinement below makes the final call */
+  o->dist = dist;
+  v3scl(nB, nB, -1);                                             /* normal points from the cylinder (geom1) to the box */
+  mat_mulvec(o->normal, B->mat, nB);
+  mat_mulvec(o->pos, B->mat, P); v3add(o->pos, o->pos, B->pos);
+  refine_cyl_box(A, B, o);
+  return o->dist <= margin;
+}
+/* Two cylinders with parallel axes (the faucet's stacked discs): same separation of variables. */
+static int cyl_cyl_parallel(const Shape* A, const Shape* B, double margin, RawCon* o) {
+  double a1[3], a2[3], c[3], cr[3], u[3];
+  mat_col(a1, A->mat, 2); mat_col(a2, B->mat, 2);
+  if (fabs(v3dot(a1, a2)) < 1 - 1e-6) return -1;
+  v3sub(c, B->pos, A->pos);
+  const double cz = v3dot(c, a1), sz = cz >= 0 ? 1 : -1;
+  v3addscl(cr, c, a1, -cz);
+  const double rho = v3norm(cr);
+  if (rho > 1e-12) v3scl(u, cr, 1 / rho); else mat_col(u, A->mat, 0);
+  const double r1 = A->size[0], h1 = A->size[1], r2 = B->size[0], h2 = B->size[1];
+  const double ga = fabs(cz) - (h1 + h2), gr = rho - (r1 + r2);
+  double dist, n[3], P[3];
+  if (ga > 0 && gr > 0) {
+    dist = sqrt(ga * ga + gr * gr);
+    for (int q = 0; q < 3; q++) {
+      n[q] = (gr * u[q] + ga * sz * a1[q]) / dist;
+      const double pa = A->pos[q] + r1 * u[q] + sz * h1 * a1[q], pb = B->pos[q] - r2 * u[q] - sz * h2 * a1[q];
+      P[q] = 0.5 * (pa + pb);
+    }
+  } else if (ga > gr) {
+    dist = ga;
+    const double t0 = fmax(-r1, rho - r2), t1 = fmin(r1, rho + r2), tm = 0.5 * (t0 + t1);
+    for (int q = 0; q < 3; q++) { n[q] = sz * a1[q]; P[q] = A->pos[q] + tm * u[q] + (sz * h1 + 0.5 * ga * sz) * a1[q]; }
+  } else {
+    dist = gr;
+    const double z0 = fmax(-h1, cz - h2), z1 = fmin(h1, cz + h2), zm = 0.5 * (z0 + z1);
+    for (int q = 0; q < 3; q++) { n[q] = u[q]; P[q] = A->pos[q] + (r1 + 0.5 * gr) * u[q] + zm * a1[q]; }
+  }
+  if (dist > margin) return 0;
+  o->dist = dist; v3copy(o->normal, n); v3copy(o->pos, P);
+  return 1;
+}
+
 static int convex_convex(const Shape* A, const Shape* B, double margin, RawCon* o) {
+  if (A->type == G_CYLINDER && B->type == G_BOX) { int r = cyl_box_aligned(A, B, margin, o); if (r >= 0) return r; }
+  if (A->type == G_CYLINDER && B->type == G_CYLINDER) { int r = cyl_cyl_parallel(A, B, margin, o); if (r >= 0) return r; }
   SV s[4]; int n = 0;
   double v[3]; v3sub(v, A->pos, B->pos);
   if (v3dot(v, v) < 1e-24) { v[0] = 1; v[1] = v[2] = 0; }
@@ -718,6 +830,17 @@ static int narrowphase(const Shape* a, const Shape* b, double margin, RawCon* o)
   if (t1 == G_CAPSULE && t2 == G_BOX) return capsule_box(a, b, margin, o);
   if (t1 == G_BOX && t2 == G_BOX) return box_box(a, b, margin, o);
   return convex_convex(a, b, margin, o);
+}
+
+/* test hook: narrowphase of one pair given explicitly (tests/test_devcollide.py fuzzes the device code against it) */
+int om_narrowphase_pair(int t1, const double* pos1, const double* mat1, const double* size1, const double* vert1, int nv1,
+                        int t2, const double* pos2, const double* mat2, const double* size2, const double* vert2, int nv2,
+                        double margin, double* out) {
+  Shape a = {t1, pos1, mat1, size1, vert1, nv1}, b = {t2, pos2, mat2, size2, vert2, nv2};
+  RawCon rc[16];
+  int cnt = narrowphase(&a, &b, margin, rc);
+  for (int i = 0; i < cnt; i++) { out[7 * i] = rc[i].dist; for (int k = 0; k < 3; k++) { out[7 * i + 1 + k] = rc[i].pos[k]; out[7 * i + 4 + k] = rc[i].normal[k]; } }
+  return cnt;
 }
 
 void om_collide(const OModel* m, OData* d) {
