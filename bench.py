@@ -274,13 +274,13 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=500)      # one full 500-step episode incl. autoreset
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--benchmark", default="MT50")
     ap.add_argument("--envs-per-gpu", type=int, default=4096)
     ap.add_argument("--seed", type=int, default=42)
-    ap.add_argument("--e2e-steps", type=int, default=50)
+    ap.add_argument("--e2e-steps", type=int, default=500)
     ap.add_argument("--cpu-steps-per-env", type=int, default=600)
     ap.add_argument("--ref-steps-per-env", type=int, default=1000)
     args = ap.parse_args()

@@ -90,11 +90,18 @@ int mw_debug_dump_floats(void);
  * [3] solver iterations (sum over forward passes), [4] forward passes */
 int mw_get_counters(mw_engine*, unsigned long long* out5);
 
+/* Re-sorts the CTA launch order by the measured mean step cost of each model slot (costliest first), so that the tail of
+ * every launch is filled by cheap environments.  Results are unaffected (environments are independent).  Host-synchronising;
+ * call it after a few warm-up steps and then rarely.                                                                */
+int mw_rebalance(mw_engine*);
+
 /* per-phase SM cycle counters summed over all env steps since the last call (one warp = one env, so these are
  * warp-cycles): [0] kinematics + mass matrix, [1] collision (incl. [2]), [2] GJK/EPA pairs, [3] constraint rows,
  * [4] bias forces + unconstrained solve, [5] constraint solver, [6] integration + glue, [7] obs / reward / autoreset,
  * [8] whole step; events: [9] GJK/EPA pair calls, [10] EPA expansions, [11] GJK iterations */
 int mw_get_profile(mw_engine*, unsigned long long* out12);
+/* warp cycles each environment spent in its most recent step (host array of n_envs) */
+int mw_get_env_cost(mw_engine*, unsigned* out);
 
 #ifdef __cplusplus
 }

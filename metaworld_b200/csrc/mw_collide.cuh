@@ -21,7 +21,7 @@ enum { G_PLANE = 0, G_HFIELD, G_SPHERE, G_CAPSULE, G_ELLIPSOID, G_CYLINDER, G_BO
 struct RawCon { creal dist, pos[3], normal[3]; };
 
 struct DShape {
-  int type; creal pos[3]; creal mat[9]; creal size[3]; const float* vert; int nvert;
+  int type; creal pos[3]; creal mat[9]; creal size[3]; const float4* vert; int nvert;   // hull vertices packed xyz_ (16-byte loads)
 };
 
 // ------------------------------------------------------------------ plane pairs
@@ -393,8 +393,19 @@ DEV void support_shape(const DShape& s, const creal* dir, creal* out, int lane) 
   mat_tmulvec(dl, s.mat, dir);
   if (s.type == G_MESH) {
     creal bv = (creal)-1e30; int bi = 0;
-    for (int i = lane; i < s.nvert; i += MW_WARP) {
-      creal x = dl[0] * __ldg(s.vert + 3 * i) + dl[1] * __ldg(s.vert + 3 * i + 1) + dl[2] * __ldg(s.vert + 3 * i + 2);
+    int i = lane;
+    for (; i + 3 * MW_WARP < s.nvert; i += 4 * MW_WARP) {     // four independent 16-byte loads in flight per lane
+      const float4 p0 = __ldg(s.vert + i), p1 = __ldg(s.vert + i + MW_WARP), p2 = __ldg(s.vert + i + 2 * MW_WARP), p3 = __ldg(s.vert + i + 3 * MW_WARP);
+      const creal x0 = dl[0] * p0.x + dl[1] * p0.y + dl[2] * p0.z, x1 = dl[0] * p1.x + dl[1] * p1.y + dl[2] * p1.z;
+      const creal x2 = dl[0] * p2.x + dl[1] * p2.y + dl[2] * p2.z, x3 = dl[0] * p3.x + dl[1] * p3.y + dl[2] * p3.z;
+      if (x0 > bv) { bv = x0; bi = i; }
+      if (x1 > bv) { bv = x1; bi = i + MW_WARP; }
+      if (x2 > bv) { bv = x2; bi = i + 2 * MW_WARP; }
+      if (x3 > bv) { bv = x3; bi = i + 3 * MW_WARP; }
+    }
+    for (; i < s.nvert; i += MW_WARP) {
+      const float4 p = __ldg(s.vert + i);
+      const creal x = dl[0] * p.x + dl[1] * p.y + dl[2] * p.z;
       if (x > bv) { bv = x; bi = i; }
     }
 #pragma unroll
@@ -402,7 +413,7 @@ DEV void support_shape(const DShape& s, const creal* dir, creal* out, int lane) 
       creal ov = __shfl_xor_sync(FULLMASK, bv, o); int oi = __shfl_xor_sync(FULLMASK, bi, o);
       if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
     }
-    l[0] = __ldg(s.vert + 3 * bi); l[1] = __ldg(s.vert + 3 * bi + 1); l[2] = __ldg(s.vert + 3 * bi + 2);
+    { const float4 p = __ldg(s.vert + bi); l[0] = p.x; l[1] = p.y; l[2] = p.z; }
   } else if (s.type == G_BOX) {
     for (int i = 0; i < 3; i++) l[i] = dl[i] >= 0 ? s.size[i] : -s.size[i];
   } else if (s.type == G_CYLINDER) {
@@ -678,7 +689,8 @@ __device__ __noinline__ int convex_pair(const DShape& A, const DShape& B, creal 
   const creal ra = core_radius(A), rb = core_radius(B);
   enum { ST_GJK0 = 0, ST_GJK, ST_G1, ST_G2, ST_G3, ST_EPA, ST_DONE };
   // ---- leader state
-  SV s[4]; int n = 0; creal v[3];
+  SV* const s = (SV*)E->fd;   // the GJK simplex (4 x 72 B, lane 0 only) lives in the not-yet-used EPA face array: shared memory, not local
+  int n = 0; creal v[3];
   int st = ST_GJK0, git = 0, k = 0, sg = 0;
   int outcome = 0;          // 0 none, 1 separated result ready, 2 EPA finished (use bestf), 3 no contact
   creal ab[3] = {0, 0, 0}, gd[3] = {0, 0, 0}, nn[3] = {0, 0, 0}, vv = 0;

@@ -10,14 +10,16 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/metaworld_b200.h"
 #include "mw_tasks.cuh"
 
 #ifndef WARPS_PER_BLOCK
-#define WARPS_PER_BLOCK 6
+#define WARPS_PER_BLOCK 7
 #endif
 #define BLOCK_THREADS (WARPS_PER_BLOCK * 32)
 
@@ -34,6 +36,8 @@ struct EngineDev {
   int* diag;                                         // [n_envs][2]: contacts dropped, solver iterations
   EpaWs* epa;                                        // GJK/EPA polytope workspace, one per launched warp (global memory)
   unsigned long long* prof;                          // [12] summed cycle / event counters (mw_get_profile)
+  unsigned long long* model_cycles;                  // [n_models][2]: warp cycles, env steps (drives mw_rebalance)
+  unsigned* env_cost;                                // [n_envs] warp cycles of each env's previous step (drives the launch order)
   int n_envs, max_steps, terminate_on_success; unsigned long long seed;
 };
 
@@ -124,18 +128,19 @@ DEV unsigned long long mix64(unsigned long long x) {
 
 // ---------------------------------------------------------------- kernels
 __global__ void __launch_bounds__(BLOCK_THREADS, 1)
-k_step(EngineDev e, const int* __restrict__ block_model, const int* __restrict__ block_start, const int* __restrict__ block_count,
+k_step(EngineDev e, const int* __restrict__ block_order, const int* __restrict__ block_model, const int* __restrict__ block_start, const int* __restrict__ block_count,
        const int* __restrict__ perm, const float* __restrict__ actions, float* __restrict__ obs_out, int obs_stride,
        float* __restrict__ reward, unsigned char* __restrict__ terminated, unsigned char* __restrict__ truncated,
        float* __restrict__ info_out, float* __restrict__ final_obs, float* __restrict__ final_info, const int* __restrict__ next_snapshot) {
   extern __shared__ __align__(16) unsigned char smem[];
   BlockShared* bs = (BlockShared*)smem;
   WarpShared* wsa = (WarpShared*)(smem + sizeof(BlockShared));
-  const int mi = block_model[blockIdx.x];
+  const int blk = block_order[blockIdx.x];             // launch slot -> CTA work item (costliest first, see k_order_*)
+  const int mi = block_model[blk];
   stage_model(bs, e.models + (size_t)mi * e.model_stride, (unsigned)sizeof(bs->model), e.taskconsts + mi);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp >= block_count[blockIdx.x]) return;
-  const int env = perm[block_start[blockIdx.x] + warp];
+  if (warp >= block_count[blk]) return;
+  const int env = perm[block_start[blk] + warp];
   WarpShared* ws = wsa + warp;
   ws->w.epa = e.epa + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp);
   WarpScratch* w = &ws->w;
@@ -173,10 +178,12 @@ k_step(EngineDev e, const int* __restrict__ block_model, const int* __restrict__
     ws->info[7] = (term || trunc) ? 1.f : 0.f;
     e.diag[2 * env] += dropped; e.diag[2 * env + 1] += iters;
     w->prof[7] = clock64() - t_phys; w->prof[8] = clock64() - t_begin;
+    e.env_cost[env] = (unsigned)(w->prof[8] > 0xFFFFFFFFll ? 0xFFFFFFFFll : w->prof[8]);
     w->prof[6] = w->prof[8] - w->prof[7] - (w->prof[0] + w->prof[1] + w->prof[3] + w->prof[4] + w->prof[5]);   // euler + glue
   }
   SYNCW();
   if (lane < 12 && e.prof) atomicAdd(e.prof + lane, (unsigned long long)w->prof[lane]);
+  if (lane == 0 && e.model_cycles) { atomicAdd(e.model_cycles + 2 * mi, (unsigned long long)w->prof[8]); atomicAdd(e.model_cycles + 2 * mi + 1, 1ull); }
   done = ws->info[7] != 0.f;
   if (lane < INFO_N) info_out[(size_t)env * INFO_N + lane] = ws->info[lane];
   if (!done) {
@@ -311,6 +318,52 @@ k_substeps(EngineDev e, const int* __restrict__ block_model, const int* __restri
   store_env(ws, e.state + env, lane);
 }
 
+// ---------------------------------------------------------------- launch-order maintenance
+// Environments differ several-fold in step cost (contacts, GJK/EPA, solver iterations) and a CTA holds its SM until its
+// slowest warp is done.  Cost is strongly correlated from one step to the next, so before every step (a) the envs of each
+// model are sorted by their previous cost, which makes CTAs homogeneous, and (b) the CTAs are sorted by the cost of their
+// first (= costliest) env, so the hardware's in-order CTA dispatch is longest-processing-time-first.  Pure scheduling:
+// results do not depend on the order.
+#define MW_SORT_MAX 8192
+DEV void bitonic_sort_u64(unsigned long long* k, int P) {
+  for (int size = 2; size <= P; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < P / 2; i += blockDim.x) {
+        int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+        bool up = (lo & size) == 0;
+        unsigned long long a = k[lo], b = k[hi];
+        if ((a > b) == up) { k[lo] = b; k[hi] = a; }
+      }
+    }
+  __syncthreads();
+}
+__global__ void k_order_envs(const int* __restrict__ model_first, const int* __restrict__ model_count, int* __restrict__ perm, const unsigned* __restrict__ env_cost) {
+  extern __shared__ unsigned long long keys[];
+  const int first = model_first[blockIdx.x], n = model_count[blockIdx.x];
+  if (n <= 1 || n > MW_SORT_MAX) return;
+  int P = 1; while (P < n) P <<= 1;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    unsigned long long key = ~0ull;
+    if (i < n) { int env = perm[first + i]; key = ((unsigned long long)(0xFFFFFFFFu - env_cost[env]) << 32) | (unsigned)env; }
+    keys[i] = key;
+  }
+  bitonic_sort_u64(keys, P);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) perm[first + i] = (int)(keys[i] & 0xFFFFFFFFull);
+}
+__global__ void k_order_blocks(int n_blocks, const int* __restrict__ block_start, const int* __restrict__ perm, const unsigned* __restrict__ env_cost, int* __restrict__ block_order) {
+  extern __shared__ unsigned long long keys[];
+  if (n_blocks > MW_SORT_MAX) { for (int i = threadIdx.x; i < n_blocks; i += blockDim.x) block_order[i] = i; return; }
+  int P = 1; while (P < n_blocks) P <<= 1;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    unsigned long long key = ~0ull;
+    if (i < n_blocks) key = ((unsigned long long)(0xFFFFFFFFu - env_cost[perm[block_start[i]]]) << 32) | (unsigned)i;
+    keys[i] = key;
+  }
+  bitonic_sort_u64(keys, P);
+  for (int i = threadIdx.x; i < n_blocks; i += blockDim.x) block_order[i] = (int)(keys[i] & 0xFFFFFFFFull);
+}
+
 // ---------------------------------------------------------------- host side
 struct mw_engine {
   int device = 0, n_models = 0, n_envs = 0, model_stride = 0;
@@ -319,22 +372,28 @@ struct mw_engine {
   MwEnvState* d_state = nullptr; MwSnapshot* d_snaps = nullptr; int snap_cap = 0, n_snaps = 0;
   int *d_goal_first = nullptr, *d_goal_count = nullptr, *d_diag = nullptr;
   EpaWs* d_epa = nullptr; size_t epa_cap = 0;
-  unsigned long long* d_prof = nullptr;
+  unsigned long long* d_prof = nullptr; unsigned long long* d_model_cycles = nullptr;
+  unsigned* d_env_cost = nullptr; int *d_block_order = nullptr, *d_model_first = nullptr, *d_model_count = nullptr; int n_sorted_models = 0;
+  std::vector<int> env_model; std::vector<int> model_order;   // block table inputs (mw_rebalance re-sorts the models by measured cost)
   // env block table
   int n_blocks = 0; int *d_block_model = nullptr, *d_block_start = nullptr, *d_block_count = nullptr, *d_perm = nullptr;
   int max_steps = 500, terminate_on_success = 0; unsigned long long seed = 0;
   unsigned long long launches = 0, env_steps = 0;
   EngineDev dev() const {
     EngineDev e; e.models = d_models; e.model_stride = model_stride; e.taskconsts = d_tc; e.meshverts = d_meshptrs;
-    e.state = d_state; e.snaps = d_snaps; e.goal_first = d_goal_first; e.goal_count = d_goal_count; e.diag = d_diag; e.epa = d_epa; e.prof = d_prof;
+    e.state = d_state; e.snaps = d_snaps; e.goal_first = d_goal_first; e.goal_count = d_goal_count; e.diag = d_diag; e.epa = d_epa; e.prof = d_prof; e.model_cycles = d_model_cycles; e.env_cost = d_env_cost;
     e.n_envs = n_envs; e.max_steps = max_steps; e.terminate_on_success = terminate_on_success; e.seed = seed; return e;
   }
 };
 
 // group work items by model into CTAs of WARPS_PER_BLOCK warps
-static void make_blocks(int n_models, const std::vector<int>& item_model, std::vector<int>& bm, std::vector<int>& bstart, std::vector<int>& bcount, std::vector<int>& perm) {
+// `order` (optional): models in launch order -- the costliest first, so that the hardware's in-order CTA dispatch behaves
+// like longest-processing-time-first list scheduling and the cheap CTAs fill the tail
+static void make_blocks(int n_models, const std::vector<int>& item_model, std::vector<int>& bm, std::vector<int>& bstart, std::vector<int>& bcount, std::vector<int>& perm,
+                        const std::vector<int>* order = nullptr) {
   bm.clear(); bstart.clear(); bcount.clear(); perm.clear();
-  for (int mi = 0; mi < n_models; mi++) {
+  for (int oi = 0; oi < n_models; oi++) {
+    const int mi = order && (int)order->size() == n_models ? (*order)[oi] : oi;
     int first = (int)perm.size();
     for (int i = 0; i < (int)item_model.size(); i++) if (item_model[i] == mi) perm.push_back(i);
     int cnt = (int)perm.size() - first;
@@ -355,6 +414,24 @@ template <class T> static int upload(T** dst, const std::vector<T>& v) {
   *dst = nullptr;
   CK(cudaMalloc((void**)dst, sizeof(T) * (v.size() ? v.size() : 1)));
   if (!v.empty()) CK(cudaMemcpy(*dst, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// (re)builds and uploads the CTA table of the environment set + the buffers of the launch-order kernels
+static int upload_env_blocks(mw_engine* E) {
+  std::vector<int> bm, bs, bc, perm;
+  make_blocks(E->n_models, E->env_model, bm, bs, bc, perm, &E->model_order);
+  E->n_blocks = (int)bm.size();
+  if (ensure_epa(E, bm.size())) return MW_ERR_CUDA;
+  if (upload(&E->d_block_model, bm) || upload(&E->d_block_start, bs) || upload(&E->d_block_count, bc) || upload(&E->d_perm, perm)) return MW_ERR_CUDA;
+  std::vector<int> mfirst, mcount, order(bm.size());
+  for (size_t b = 0; b < bm.size(); b++) {
+    order[b] = (int)b;
+    if (b == 0 || bm[b] != bm[b - 1]) { mfirst.push_back(bs[b]); mcount.push_back(0); }
+    mcount.back() += bc[b];
+  }
+  E->n_sorted_models = (int)mfirst.size();
+  if (upload(&E->d_model_first, mfirst) || upload(&E->d_model_count, mcount) || upload(&E->d_block_order, order)) return MW_ERR_CUDA;
   return 0;
 }
 
@@ -391,14 +468,22 @@ int mw_create(mw_engine** out, int device, int n_models, const void* models, con
   for (int i = 0; i < n_models; i++) {
     int nvt = nmeshvert ? nmeshvert[i] : 0;
     float* p = nullptr;
-    CK(cudaMalloc((void**)&p, sizeof(float) * 3 * (nvt > 0 ? nvt : 1)));
-    if (nvt > 0) CK(cudaMemcpy(p, meshverts[i], sizeof(float) * 3 * nvt, cudaMemcpyHostToDevice));
+    CK(cudaMalloc((void**)&p, sizeof(float) * 4 * (nvt > 0 ? nvt : 1)));
+    if (nvt > 0) {   // repack xyz -> xyz_ so that a support query reads one 16-byte word per vertex
+      std::vector<float> packed(4 * (size_t)nvt, 0.f);
+      for (int v = 0; v < nvt; v++) for (int c = 0; c < 3; c++) packed[4 * v + c] = meshverts[i][3 * v + c];
+      CK(cudaMemcpy(p, packed.data(), sizeof(float) * 4 * nvt, cudaMemcpyHostToDevice));
+    }
     ptrs[i] = p; E->meshbufs.push_back(p);
   }
   CK(cudaMalloc((void**)&E->d_meshptrs, sizeof(float*) * n_models));
   CK(cudaMemcpy(E->d_meshptrs, ptrs.data(), sizeof(float*) * n_models, cudaMemcpyHostToDevice));
+  CK(cudaMalloc((void**)&E->d_model_cycles, sizeof(unsigned long long) * 2 * n_models));
+  CK(cudaMemset(E->d_model_cycles, 0, sizeof(unsigned long long) * 2 * n_models));
   CK(cudaMalloc((void**)&E->d_prof, sizeof(unsigned long long) * 12));
   CK(cudaMemset(E->d_prof, 0, sizeof(unsigned long long) * 12));
+  CK(cudaFuncSetAttribute(k_order_envs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned long long) * MW_SORT_MAX)));
+  CK(cudaFuncSetAttribute(k_order_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned long long) * MW_SORT_MAX)));
   CK(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
   CK(cudaFuncSetAttribute(k_snapshot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
   CK(cudaFuncSetAttribute(k_substeps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
@@ -411,7 +496,7 @@ void mw_destroy(mw_engine* E) {
   cudaSetDevice(E->device);
   cudaFree(E->d_models); cudaFree(E->d_tc); cudaFree(E->d_meshptrs);
   for (float* p : E->meshbufs) cudaFree(p);
-  cudaFree(E->d_state); cudaFree(E->d_snaps); cudaFree(E->d_goal_first); cudaFree(E->d_goal_count); cudaFree(E->d_diag); cudaFree(E->d_epa); cudaFree(E->d_prof);
+  cudaFree(E->d_state); cudaFree(E->d_snaps); cudaFree(E->d_goal_first); cudaFree(E->d_goal_count); cudaFree(E->d_diag); cudaFree(E->d_epa); cudaFree(E->d_prof); cudaFree(E->d_model_cycles); cudaFree(E->d_env_cost); cudaFree(E->d_block_order); cudaFree(E->d_model_first); cudaFree(E->d_model_count);
   cudaFree(E->d_block_model); cudaFree(E->d_block_start); cudaFree(E->d_block_count); cudaFree(E->d_perm);
   delete E;
 }
@@ -421,10 +506,12 @@ int mw_set_envs(mw_engine* E, int n_envs, const int* env_model) {
   CK(cudaSetDevice(E->device));
   std::vector<int> im(env_model, env_model + n_envs), bm, bs, bc, perm;
   for (int v : im) if (v < 0 || v >= E->n_models) return fail(MW_ERR_ARG, "mw_set_envs: model index out of range");
-  make_blocks(E->n_models, im, bm, bs, bc, perm);
-  E->n_envs = n_envs; E->n_blocks = (int)bm.size();
-  if (ensure_epa(E, bm.size())) return MW_ERR_CUDA;
-  if (upload(&E->d_block_model, bm) || upload(&E->d_block_start, bs) || upload(&E->d_block_count, bc) || upload(&E->d_perm, perm)) return MW_ERR_CUDA;
+  E->env_model = im;
+  E->n_envs = n_envs;
+  if (upload_env_blocks(E)) return MW_ERR_CUDA;
+  if (E->d_env_cost) cudaFree(E->d_env_cost);
+  CK(cudaMalloc((void**)&E->d_env_cost, sizeof(unsigned) * n_envs));
+  CK(cudaMemset(E->d_env_cost, 0, sizeof(unsigned) * n_envs));
   if (E->d_state) cudaFree(E->d_state);
   CK(cudaMalloc((void**)&E->d_state, sizeof(MwEnvState) * n_envs));
   CK(cudaMemset(E->d_state, 0, sizeof(MwEnvState) * n_envs));
@@ -500,10 +587,16 @@ int mw_step(mw_engine* E, const float* actions, float* obs, int obs_stride, floa
   if (!actions || !obs || !reward || !terminated || !truncated || !info || obs_stride < 39) return fail(MW_ERR_ARG, "mw_step: bad arguments");
   if (!next_snapshot && !E->d_goal_first) return fail(MW_ERR_STATE, "mw_step: no next_snapshot and no goal sets for the device sampler");
   CK(cudaSetDevice(E->device));
-  k_step<<<E->n_blocks, BLOCK_THREADS, smem_bytes(), (cudaStream_t)stream>>>(E->dev(), E->d_block_model, E->d_block_start, E->d_block_count, E->d_perm,
+  {   // launch order from the previous step's per-env cost (see k_order_*)
+    int Pm = 1; while (Pm < E->n_envs && Pm < MW_SORT_MAX) Pm <<= 1;
+    int Pb = 1; while (Pb < E->n_blocks && Pb < MW_SORT_MAX) Pb <<= 1;
+    k_order_envs<<<E->n_sorted_models, 1024, sizeof(unsigned long long) * Pm, (cudaStream_t)stream>>>(E->d_model_first, E->d_model_count, E->d_perm, E->d_env_cost);
+    k_order_blocks<<<1, 1024, sizeof(unsigned long long) * Pb, (cudaStream_t)stream>>>(E->n_blocks, E->d_block_start, E->d_perm, E->d_env_cost, E->d_block_order);
+  }
+  k_step<<<E->n_blocks, BLOCK_THREADS, smem_bytes(), (cudaStream_t)stream>>>(E->dev(), E->d_block_order, E->d_block_model, E->d_block_start, E->d_block_count, E->d_perm,
       actions, obs, obs_stride, reward, terminated, truncated, info, final_obs, final_info, next_snapshot);
   CK(cudaGetLastError());
-  E->launches++; E->env_steps += (unsigned long long)E->n_envs;
+  E->launches += 3; E->env_steps += (unsigned long long)E->n_envs;
   return MW_OK;
 }
 
@@ -557,6 +650,29 @@ int mw_get_counters(mw_engine* E, unsigned long long* out5) {
   for (int i = 0; i < E->n_envs; i++) { dropped += diag[2 * i]; iters += diag[2 * i + 1]; }
   out5[0] = E->launches; out5[1] = E->env_steps; out5[2] = dropped; out5[3] = iters; out5[4] = E->env_steps * 6ull;
   E->launches = 0; E->env_steps = 0;
+  return MW_OK;
+}
+
+int mw_rebalance(mw_engine* E) {
+  if (!E || !E->d_state) return fail(MW_ERR_STATE, "mw_rebalance: mw_set_envs not called");
+  CK(cudaSetDevice(E->device));
+  CK(cudaDeviceSynchronize());
+  std::vector<unsigned long long> mc(2 * (size_t)E->n_models);
+  CK(cudaMemcpy(mc.data(), E->d_model_cycles, sizeof(unsigned long long) * mc.size(), cudaMemcpyDeviceToHost));
+  CK(cudaMemset(E->d_model_cycles, 0, sizeof(unsigned long long) * mc.size()));
+  std::vector<std::pair<double, int>> cost;
+  for (int i = 0; i < E->n_models; i++) cost.push_back({mc[2 * i + 1] ? (double)mc[2 * i] / (double)mc[2 * i + 1] : 0.0, i});
+  std::stable_sort(cost.begin(), cost.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first > b.first; });
+  E->model_order.clear();
+  for (auto& c : cost) E->model_order.push_back(c.second);
+  if (upload_env_blocks(E)) return MW_ERR_CUDA;
+  return MW_OK;
+}
+
+int mw_get_env_cost(mw_engine* E, unsigned* out) {
+  if (!E || !out || !E->d_env_cost) return fail(MW_ERR_ARG, "mw_get_env_cost");
+  CK(cudaSetDevice(E->device));
+  CK(cudaMemcpy(out, E->d_env_cost, sizeof(unsigned) * E->n_envs, cudaMemcpyDeviceToHost));
   return MW_OK;
 }
 

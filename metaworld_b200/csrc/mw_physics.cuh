@@ -17,16 +17,16 @@
 #define MW_MAXCON 48
 #endif
 #define MW_MAXSCALAR 24      // weld (6) + joint-limit rows
-#define MW_MAXEFC (MW_MAXSCALAR + 4 * MW_MAXCON)
+#define MW_MAXEFC (MW_MAXSCALAR + 4 * MW_MAXCON)   // worst case: every contact condim 4
 
 enum { JT_FREE = 0, JT_BALL, JT_SLIDE, JT_HINGE };
 
 struct Contact {
-  real pos[3], frame[9], dist, mu, fr1, fr3, incl;
-  real solref[2], solimp[5];
+  real pos[3], frame[9], dist, mu, fr1, fr3;
   real H[10];              // packed symmetric dim x dim cone Hessian (row-major upper)
   real fn;                 // normal force of the last solve
-  int dim, g1, g2, row, hzone;
+  short row, prm;          // first efc row (-1: not instantiated), index into MwModel.param (margin, solref, solimp ...)
+  unsigned char dim, g1, g2, hzone;
 };
 
 // region U is time-shared: (a) geom world poses + EPA workspace during collision, (b) efc_J afterwards
@@ -44,7 +44,7 @@ struct WarpScratch {
   real M[MW_MAXDOF * NVP], H[MW_MAXDOF * NVP];
   alignas(16) real U[MW_UWORDS];
   EpaWs* epa;               // this warp's GJK/EPA polytope workspace (global memory, see mw_engine.cu)
-  real eD[MW_MAXEFC], eAref[MW_MAXEFC], eJar[MW_MAXEFC], eJv[MW_MAXEFC], eF[MW_MAXEFC], eHd[MW_MAXEFC];
+  real eD[MW_MAXEFC], eAref[MW_MAXEFC], eJar[MW_MAXEFC], eJv[MW_MAXEFC], eF[MW_MAXEFC], eHd[MW_MAXSCALAR];
   Contact con[MW_MAXCON];
   unsigned short cand[64];
   int ncon, nefc, nscalar, nweld, solver_iter, ncon_dropped;
@@ -308,7 +308,7 @@ DEV void mw_load_shape(const MwModel* m, const creal* gpose, const float* meshve
   s->type = m->geom_type[g];
   for (int i = 0; i < 3; i++) { s->pos[i] = gpose[12 * g + i]; s->size[i] = m->geom_size[g][i]; }
   for (int i = 0; i < 9; i++) s->mat[i] = gpose[12 * g + 3 + i];
-  s->vert = meshvert + 3 * m->geom_meshadr[g]; s->nvert = m->geom_meshnum[g];
+  s->vert = (const float4*)meshvert + m->geom_meshadr[g]; s->nvert = m->geom_meshnum[g];
 }
 DEV void make_frame(creal* fr) {
   v3normalize(fr);
@@ -330,9 +330,7 @@ DEV void mw_store_contact(const MwModel* m, WarpScratch* w, int slot, const RawC
   for (int k = 0; k < 3; k++) c->pos[k] = (real)rc.pos[k];
   for (int k = 0; k < 9; k++) c->frame[k] = (real)fr[k];
   c->g1 = m->pair_g1[pair]; c->g2 = m->pair_g2[pair];
-  c->incl = P[1]; c->dim = (int)P[2]; c->fr1 = P[3]; c->fr3 = P[4]; c->mu = P[3];
-  c->solref[0] = P[5]; c->solref[1] = P[6];
-  for (int k = 0; k < 5; k++) c->solimp[k] = P[7 + k];
+  c->prm = (short)prm; c->dim = (unsigned char)P[2]; c->fr1 = P[3]; c->fr3 = P[4]; c->mu = P[3];
   c->row = -1; c->fn = 0; c->hzone = 0;
 }
 
@@ -507,7 +505,8 @@ __device__ __noinline__ void mw_make_constraints(const MwModel* __restrict__ m, 
   const int ncon = w->ncon;
   for (int c = 0; c < ncon; c++) {
     Contact* con = &w->con[c];
-    if (con->dist >= con->incl || nefc + con->dim > MW_MAXEFC) { if (lane == 0) con->row = -1; continue; }
+    if (con->dist >= (real)m->param[con->prm][1]) { if (lane == 0) con->row = -1; continue; }
+    if (nefc + con->dim > MW_MAXEFC) { if (lane == 0) { con->row = -1; w->ncon_dropped++; } continue; }   // counted, reported by mw_get_counters
     int l1 = m->geom_link[con->g1], l2 = m->geom_link[con->g2];
     unsigned m1 = l1 < 0 ? 0u : m->link_dofmask[l1], m2 = l2 < 0 ? 0u : m->link_dofmask[l2];
     real p[3] = {con->pos[0], con->pos[1], con->pos[2]};
@@ -548,8 +547,10 @@ __device__ __noinline__ void mw_make_constraints(const MwModel* __restrict__ m, 
     int r0 = con->row, dim = con->dim;
     real tran = m->geom_invw[con->g1][0] + m->geom_invw[con->g2][0];
     real rot = m->geom_invw[con->g1][1] + m->geom_invw[con->g2][1];
-    RowParam rp = mw_impedance(con->dist - con->incl, con->solref, con->solimp, h);
-    RowParam rf = mw_impedance((real)0, con->solref, con->solimp, h);
+    const float* Pm = m->param[con->prm];
+    const real incl = Pm[1], solref[2] = {Pm[5], Pm[6]}, solimp[5] = {Pm[7], Pm[8], Pm[9], Pm[10], Pm[11]};
+    RowParam rp = mw_impedance(con->dist - incl, solref, solimp, h);
+    RowParam rf = mw_impedance((real)0, solref, solimp, h);
     real R0 = fmax(MW_EPS, (1 - rp.imp) * tran / rp.imp);
     (void)rot;
     real R1 = R0 / m->impratio;
@@ -558,7 +559,7 @@ __device__ __noinline__ void mw_make_constraints(const MwModel* __restrict__ m, 
     for (int k = 0; k < dim; k++) {
       real vel = 0; for (int d = 0; d < nv; d++) vel += J[(r0 + k) * NVP + d] * w->qvel[d];
       w->eD[r0 + k] = 1 / Rk[k];
-      w->eAref[r0 + k] = k == 0 ? (-rp.B * vel - rp.K * rp.imp * (con->dist - con->incl)) : (-rf.B * vel);
+      w->eAref[r0 + k] = k == 0 ? (-rp.B * vel - rp.K * rp.imp * (con->dist - incl)) : (-rf.B * vel);
     }
   }
   if (lane == 0) { w->nefc = nefc; w->nscalar = nscalar; w->nweld = 6; }

@@ -62,6 +62,8 @@ def _load(path):
     L.mw_get_counters.argtypes = [vp, vp]
     L.mw_debug_forward.argtypes = [vp, vp, vp, vp]
     L.mw_get_profile.argtypes = [vp, vp]
+    L.mw_rebalance.argtypes = [vp]
+    L.mw_get_env_cost.argtypes = [vp, vp]
     assert L.mw_sizeof_model() == lower.DTYPE.itemsize, "MwModel layout mismatch (rebuild the library)"
     assert L.mw_sizeof_taskconst() == TASKCONST_DTYPE.itemsize
     assert L.mw_sizeof_envstate() == ENVSTATE_DTYPE.itemsize == 512
@@ -259,6 +261,16 @@ class Engine:
         self.torch.cuda.synchronize(self.device)
         _ck(lib().mw_get_profile(self.h, out.ctypes.data))
         return dict(zip(self.PROFILE_KEYS, (int(x) for x in out)))
+
+    def env_cost(self):
+        out = np.zeros(self.n_envs, dtype=np.uint32)
+        self.torch.cuda.synchronize(self.device)
+        _ck(lib().mw_get_env_cost(self.h, out.ctypes.data))
+        return out
+
+    def rebalance(self):
+        """Launch the costliest task types first (measured); see mw_rebalance."""
+        _ck(lib().mw_rebalance(self.h))
 
     def counters(self):
         out = np.zeros(5, dtype=np.uint64)

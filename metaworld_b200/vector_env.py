@@ -180,6 +180,7 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
         self.d_actions.copy_(self.h_actions, non_blocking=True)
         self.engine.step(self.d_actions, self.d_obs, self.d_reward, self.d_term, self.d_trunc, self.d_info,
                          self.d_final_obs, self.d_final_info, self.d_next)
+        self._maybe_rebalance()
         small = t.cat([self.d_reward[:, None], self.d_info, (self.d_term + 2 * self.d_trunc).float()[:, None]], dim=1)
         self.h_small.copy_(small, non_blocking=True)
         self.h_obs.copy_(self.d_obs, non_blocking=True)
@@ -218,6 +219,11 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
             self._push_next()
         return obs, reward, terminated, truncated, infos
 
+    def _maybe_rebalance(self):
+        """Task types differ several-fold in step cost; after a few measured steps (and then rarely) the engine re-sorts
+        its CTA launch order costliest-first (mw_rebalance).  Results do not depend on the order."""
+        return   # superseded: the engine now re-sorts its launch order on the device before every step (k_order_*)
+
     def step_async(self, actions):
         self._pending_actions = actions
 
@@ -242,6 +248,7 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
         nxt = None if getattr(self, "_device_sampler", False) else self.d_next
         self.engine.step(actions, self.d_obs, self.d_reward, self.d_term, self.d_trunc, self.d_info, self.d_final_obs,
                          self.d_final_info, nxt)
+        self._maybe_rebalance()
         return self.d_obs, self.d_reward, self.d_term, self.d_trunc, self.d_info
 
     # attribute RPC used by metaworld/evaluation.py:48-169 and the reference tests

@@ -49,6 +49,34 @@ def contacts(rig, task, rv, k, qpos, qvel, mocap, action, nsub=5):
         rig.eng.debug_substeps(1, ctrl); P.mj_step(oe.model, oe.data, 1)
 
 
+def do_first(task):
+    """first env step after reset, substep by substep (device snapshot state vs oracle reset state)"""
+    g = np.load(os.path.join(GOLD, f"traj_{task}.npz"))
+    rig = Rig(torch, task, g["rand_vec"]); rig.reset()
+    k = 0
+    st = rig.eng.get_state()
+    nq, nv = g["reset_qpos"].shape[1], g["reset_qvel"].shape[1]
+    oe = OT[task](); n = len(oe.random_reset_space()[0]); oe.set_task_vec(g["rand_vec"][k][:n], False); oe.reset()
+    print(f"{task}: reset state: qpos {big(st[k]['qpos'][:nq], oe.data.qpos, 1e-7)} | qvel {big(st[k]['qvel'][:nv], oe.data.qvel, 1e-6)} | warm {big(st[k]['warm'][:nv], oe.data.qacc_warmstart, 1e-4)} | mocap {big(st[k]['mocap_pos'], oe.data.mocap_pos[0], 1e-7)}")
+    a = g["actions"][k, 0]
+    mp = np.clip(oe.data.mocap_pos[0] + np.clip(a[:3], -1, 1) * 0.01, oe.mocap_low, oe.mocap_high)
+    st[k]["mocap_pos"] = mp; rig.eng.set_state(st)
+    oe.data.mocap_pos[0][:] = mp; oe.data.mocap_quat[0][:] = [1, 0, 1, 0]
+    ctrl = (float(a[3]), -float(a[3])); oe.data.ctrl = ctrl
+    for sub in range(5):
+        con, qacc, meta = rig.eng.debug_forward(ctrl)
+        P.mj_forward(oe.model, oe.data)
+        qe = np.abs(qacc[k, :nv] - oe.data.qacc).max()
+        print(f'  substep {sub}: dev ncon {int(meta[k,0])} nefc {int(meta[k,1])} it {int(meta[k,2])} | ora ncon {oe.data.ncon} nefc {oe.data.nefc} it {oe.data.solver_iter} | qacc err {qe:.3e}')
+        oc = sorted([(c.geom1, c.geom2, c.dist, *c.pos, *list(c.frame)[:3], oe.data.efc_force[c.efc_address] if c.efc_address >= 0 else 0) for c in oe.data.contact])
+        dc = sorted([(int(c[7]), int(c[8]), c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[9]) for c in con[k][: int(meta[k, 0])]])
+        for x in dc: print('    dev', np.array(x))
+        for x in oc: print('    ora', np.array(x))
+        print('    dev qacc', qacc[k, :nv]); print('    ora qacc', oe.data.qacc)
+        rig.eng.debug_substeps(1, ctrl); P.mj_step(oe.model, oe.data, 1)
+        st2 = rig.eng.get_state(); print('    qpos err', big(st2[k]['qpos'][:nq], oe.data.qpos, 1e-6))
+
+
 def do_reset(task):
     g = np.load(os.path.join(GOLD, f"traj_{task}.npz"))
     rig = Rig(torch, task, g["rand_vec"]); snaps = rig.eng.get_snapshots()
@@ -97,6 +125,6 @@ if __name__ == "__main__":
     mode = sys.argv[1]
     for task in sys.argv[2:]:
         try:
-            dict(reset=do_reset, open=do_open, cr=do_cr)[mode](task)
+            dict(reset=do_reset, open=do_open, cr=do_cr, first=do_first)[mode](task)
         except Exception as ex:  # keep going: this is a survey tool
             print(f"{task}: {mode} raised {ex!r}")

@@ -6,7 +6,8 @@ from metaworld_b200.vector_env import MetaWorldVecEnv
 from metaworld_b200 import benchmarks as B
 from metaworld_b200.tasks import TASKS
 names = sys.argv[1:] or list(TASKS)
-N, K = 888, 20
+import os
+N, K = int(os.environ.get("MW_N", 888)), int(os.environ.get("MW_K", 20))
 rows = []
 for n in names:
     tasks = B.make_tasks([n], False, seed=1, n_goals=10)

@@ -17,9 +17,15 @@ static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
 static inline void __syncwarp() {}
 template <class T> static inline T __ldg(const T* p) { return *p; }
+struct float4 { float x, y, z, w; };
 #include "../../metaworld_b200/csrc/mw_collide.cuh"
 
-static void load(DShape* s, int type, const double* pos, const double* mat, const double* size, const float* vert, int nvert) {
+#include <vector>
+static std::vector<float4> g_pack[2];
+static void load(DShape* s, int type, const double* pos, const double* mat, const double* size, const float* vert3, int nvert, int slot) {
+  g_pack[slot].resize(nvert > 0 ? nvert : 1);
+  for (int i = 0; i < nvert; i++) g_pack[slot][i] = float4{vert3[3 * i], vert3[3 * i + 1], vert3[3 * i + 2], 0.f};
+  const float4* vert = g_pack[slot].data();
   s->type = type;
   for (int i = 0; i < 3; i++) { s->pos[i] = pos[i]; s->size[i] = (float)size[i]; }   // sizes are float32 in MwModel
   for (int i = 0; i < 9; i++) s->mat[i] = mat[i];
@@ -29,7 +35,7 @@ static void load(DShape* s, int type, const double* pos, const double* mat, cons
 extern "C" int dev_pair(int t1, const double* pos1, const double* mat1, const double* size1, const float* vert1, int nv1,
                         int t2, const double* pos2, const double* mat2, const double* size2, const float* vert2, int nv2,
                         double margin, double* out /* [8][7]: dist, pos, normal */) {
-  DShape a, b; load(&a, t1, pos1, mat1, size1, vert1, nv1); load(&b, t2, pos2, mat2, size2, vert2, nv2);
+  DShape a, b; load(&a, t1, pos1, mat1, size1, vert1, nv1, 0); load(&b, t2, pos2, mat2, size2, vert2, nv2, 1);
   RawCon rc[8]; int cnt = 0;
   static EpaSm E; static EpaWs W;
   if (pair_is_analytic(t1, t2)) cnt = narrow_analytic(a, b, margin, rc);
