@@ -454,18 +454,16 @@ DEV void closest_tri(const creal* a, const creal* b, const creal* c, creal* w) {
   w[1] = vb * den; w[2] = vc * den; w[0] = 1 - w[1] - w[2];
 }
 // simplex reduction (leader lane only). returns true if the origin is enclosed by a tetrahedron
-__device__ __noinline__ bool closest_simplex(SV* s, int* n, creal* v) {
+// Whole warp calls this (the simplex lives in shared memory); *n and v are meaningful on lane 0.  The four faces of a
+// tetrahedron are examined by four lanes at once; the winner is the face with the smallest distance, lowest index on
+// ties -- the same choice as a serial scan.
+__device__ __noinline__ bool closest_simplex(SV* s, int* n, creal* v, int lane) {
   creal w[4] = {0, 0, 0, 0};
-  if (*n == 1) w[0] = 1;
-  else if (*n == 2) {
-    creal ab[3]; v3sub(ab, s[1].v, s[0].v);
-    creal t = -v3dot(s[0].v, ab) / fmax(v3dot(ab, ab), (creal)1e-300);
-    if (t <= 0) w[0] = 1; else if (t >= 1) w[1] = 1; else { w[0] = 1 - t; w[1] = t; }
-  } else if (*n == 3) closest_tri(s[0].v, s[1].v, s[2].v, w);
-  else {
+  const int nn = __shfl_sync(FULLMASK, *n, 0);
+  if (nn == 4) {
     const int F[4][4] = {{0, 1, 2, 3}, {0, 2, 3, 1}, {0, 3, 1, 2}, {1, 3, 2, 0}};
-    creal best = (creal)1e30; bool found = false; creal bw[4] = {0, 0, 0, 0};
-    for (int f = 0; f < 4; f++) {
+    creal best = (creal)1e30; int bf = 4; creal btw[3] = {0, 0, 0};
+    for (int f = lane; f < 4; f += MW_WARP) {
       const creal *a = s[F[f][0]].v, *b = s[F[f][1]].v, *c = s[F[f][2]].v, *dv = s[F[f][3]].v;
       creal ab[3], ac[3], nrm[3], ad[3]; v3sub(ab, b, a); v3sub(ac, c, a); v3cross(nrm, ab, ac); v3sub(ad, dv, a);
       creal sd = v3dot(nrm, ad), so = -v3dot(nrm, a);
@@ -474,14 +472,29 @@ __device__ __noinline__ bool closest_simplex(SV* s, int* n, creal* v) {
       creal tw[3]; closest_tri(a, b, c, tw);
       creal q[3]; for (int k = 0; k < 3; k++) q[k] = tw[0] * a[k] + tw[1] * b[k] + tw[2] * c[k];
       creal dd = v3dot(q, q);
-      if (dd < best) { best = dd; found = true; bw[0] = bw[1] = bw[2] = bw[3] = 0; bw[F[f][0]] = tw[0]; bw[F[f][1]] = tw[1]; bw[F[f][2]] = tw[2]; }
+      if (dd < best) { best = dd; bf = f; btw[0] = tw[0]; btw[1] = tw[1]; btw[2] = tw[2]; }
     }
-    if (!found) { v3zero(v); return true; }
-    for (int i = 0; i < 4; i++) w[i] = bw[i];
+#pragma unroll
+    for (int x = 2; x > 0; x >>= 1) {
+      const creal ob = __shfl_xor_sync(FULLMASK, best, x); const int of = __shfl_xor_sync(FULLMASK, bf, x);
+      const creal o0 = __shfl_xor_sync(FULLMASK, btw[0], x), o1 = __shfl_xor_sync(FULLMASK, btw[1], x), o2 = __shfl_xor_sync(FULLMASK, btw[2], x);
+      if (of < 4 && (bf >= 4 || ob < best || (ob == best && of < bf))) { best = ob; bf = of; btw[0] = o0; btw[1] = o1; btw[2] = o2; }
+    }
+    if (bf >= 4) { if (lane == 0) v3zero(v); return true; }     // no face sees the origin: enclosed
+    w[F[bf][0]] = btw[0]; w[F[bf][1]] = btw[1]; w[F[bf][2]] = btw[2];
+  } else if (lane == 0) {
+    if (nn == 1) w[0] = 1;
+    else if (nn == 2) {
+      creal ab[3]; v3sub(ab, s[1].v, s[0].v);
+      creal t = -v3dot(s[0].v, ab) / fmax(v3dot(ab, ab), (creal)1e-300);
+      if (t <= 0) w[0] = 1; else if (t >= 1) w[1] = 1; else { w[0] = 1 - t; w[1] = t; }
+    } else closest_tri(s[0].v, s[1].v, s[2].v, w);
   }
-  int m = 0; v3zero(v);
-  for (int i = 0; i < *n; i++) if (w[i] > 0) { for (int k = 0; k < 3; k++) v[k] += w[i] * s[i].v[k]; if (m != i) s[m] = s[i]; m++; }
-  *n = m;
+  if (lane == 0) {
+    int m = 0; v3zero(v);
+    for (int i = 0; i < nn; i++) if (w[i] > 0) { for (int k = 0; k < 3; k++) v[k] += w[i] * s[i].v[k]; if (m != i) s[m] = s[i]; m++; }
+    *n = m;
+  }
   return false;
 }
 DEV void simplex_weights(const SV* s, int n, creal* w) {
@@ -502,6 +515,7 @@ DEV void simplex_weights(const SV* s, int n, creal* w) {
 #define EPA_MAXE 96
 #define EPA_ITERS 50
 #define EPA_TOL ((creal)1e-6)
+#define GJK_TOL ((creal)1e-8)   // absolute gap between the GJK upper and lower distance bounds
 struct EpaSm {
   creal fd[EPA_MAXF];            // face plane offsets
   creal vv[EPA_MAXV][3];         // Minkowski-difference vertices
@@ -735,21 +749,18 @@ __device__ __noinline__ int convex_pair(const DShape& A, const DShape& B, creal 
     creal dir[3] = {bcast(dirl[0], 0), bcast(dirl[1], 0), bcast(dirl[2], 0)};
     SV w; support_pair(A, B, dir, &w, lane);
     // ---------------- leader: consume the support point
+    int need_cs = 0;
     if (lane == 0) {
       if (st == ST_GJK0) { s[0] = w; n = 1; v3copy(v, w.v); st = ST_GJK; git = 0; }
       else if (st == ST_GJK) {
         const creal vw = v3dot(v, w.v);
-        if (vv - vw <= (creal)1e-12 * vv) GJK_FINISH()                                              // v is the closest point
+        if (vv - vw <= (creal)1e-12 * vv || vv - vw <= GJK_TOL * sqrt(vv)) GJK_FINISH()             // |v| within GJK_TOL of the lower bound: closest point found
         else if (vw > 0 && vw / sqrt(vv) - ra - rb > margin + (creal)1e-4) { outcome = 3; st = ST_DONE; }   // separating axis
         else {
           bool dup = false;
           for (int i = 0; i < n; i++) { creal t[3]; v3sub(t, s[i].v, w.v); if (v3dot(t, t) < (creal)1e-24) dup = true; }
           if (dup) GJK_FINISH()
-          else {
-            s[n++] = w;
-            if (closest_simplex(s, &n, v)) { st = ST_G1; k = 0; }
-            git++;
-          }
+          else { s[n++] = w; need_cs = 1; }
         }
       } else if (st == ST_G1) {
         creal dd[3]; v3sub(dd, w.v, s[0].v);
@@ -764,6 +775,12 @@ __device__ __noinline__ int convex_pair(const DShape& A, const DShape& B, creal 
         if (fabs(v3dot(aw, nn)) > (creal)1e-14 * sqrt(v3dot(nn, nn))) s[n++] = w;
         else sg++;
       }
+    }
+    if (__shfl_sync(FULLMASK, need_cs, 0)) {   // simplex reduction with the whole warp (tetrahedron faces in parallel)
+      __syncwarp();
+      const bool enc = closest_simplex(s, &n, v, lane);
+      if (lane == 0) { if (enc) { st = ST_G1; k = 0; } git++; }
+      __syncwarp();
     }
   }
   // ---------------- EPA expansion, warp-parallel (uniform control flow; nv, nf, bestf identical on all lanes)

@@ -502,6 +502,7 @@ static void simplex_weights(const SV* s, int n, double* w) {
 
 #define EPA_MAXV 64
 #define EPA_MAXF 320
+#define GJK_TOL 1e-8       /* absolute gap between the GJK upper and lower distance bounds */
 #define EPA_ITERS 50
 #define EPA_TOL 1e-6
 typedef struct { int v[3]; double n[3], d; int alive; } EFace;
@@ -760,7 +761,7 @@ static int convex_convex(const Shape* A, const Shape* B, double margin, RawCon* 
     double nd[3] = {-v[0], -v[1], -v[2]};
     SV w; support(A, B, nd, &w);
     double vw = v3dot(v, w.v);
-    if (vv - vw <= 1e-12 * vv) break; /* no progress: v is the closest point */
+    if (vv - vw <= 1e-12 * vv || vv - vw <= GJK_TOL * sqrt(vv)) break; /* |v| is within GJK_TOL of the lower bound v.w/|v|: v is the closest point */
     if (vw > 0 && vw / sqrt(vv) - ra - rb > margin + 1e-4) return 0; /* separating axis */
     int dup = 0;
     for (int i = 0; i < n; i++) { double t[3]; v3sub(t, s[i].v, w.v); if (v3dot(t, t) < 1e-24) dup = 1; }
