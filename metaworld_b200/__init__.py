@@ -8,6 +8,7 @@ from __future__ import annotations
 __version__ = "0.1.0"
 
 from .benchmarks import ALL_V3, ML1, ML10, ML25, ML45, MT1, MT10, MT25, MT50, Benchmark, Task, make_benchmark  # noqa: F401
+from . import evaluation  # noqa: F401  (evaluation / metalearning_evaluation, metaworld/evaluation.py)
 
 
 def make_mt_envs(*a, **k):

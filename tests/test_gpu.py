@@ -270,3 +270,22 @@ def test_full_size_properties(torch_cuda):
         assert c["contacts_dropped"] == 0
         env.close()
     assert np.array_equal(finals[0], finals[1])
+
+
+def test_evaluation_loop_on_device_envs(torch_cuda):
+    """metaworld_b200.evaluation over the real vector env: the reference's `evaluation()` protocol end to end
+    (toggle_terminate_on_success, final_info["episode"]["r"], final_info["success"], per-task bookkeeping)."""
+    from metaworld_b200.vector_env import make_mt_envs
+    from metaworld_b200 import evaluation as E
+
+    class RandomAgent:
+        def __init__(self, n): self.rng = np.random.default_rng(5); self.n = n; self.resets = 0
+        def eval_action(self, obs): return self.rng.uniform(-1, 1, size=(len(obs), 4)).astype(np.float32)
+        def reset(self, mask): self.resets += int(np.sum(mask))
+
+    env = make_mt_envs("MT10", seed=3, num_envs=20, max_episode_steps=15)
+    ag = RandomAgent(20)
+    sr, ret, per_task, rets = E.evaluation(ag, env, num_episodes=2)
+    assert set(per_task) == set(env.get_attr("task_name")) and len(per_task) == 10
+    assert all(len(v) == 2 for v in rets.values()) and 0.0 <= sr <= 1.0 and np.isfinite(ret)
+    assert ag.resets >= 20 + 2 * 10 and not any(env.get_attr("terminate_on_success"))
