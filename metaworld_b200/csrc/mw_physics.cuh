@@ -377,14 +377,17 @@ __device__ __noinline__ void mw_collide(const MwModel* __restrict__ m, const flo
         creal t[3]; v3sub(t, p2, p1);
         creal bound = r1 + r2 + margin;
         keep = v3dot(t, t) <= bound * bound;
-        if (keep && t2 == G_BOX) {   // bounding sphere of g1 against the exact box g2
-          creal cl[3], dd = 0; mat_tmulvec(cl, p2 + 3, t); // centre of g1 in box-2 frame is -R2^T t
-          for (int i = 0; i < 3; i++) { creal e = fabs(cl[i]) - m->geom_size[g2][i]; if (e > 0) dd += e * e; }
+        // bounding sphere of one geom against the oriented bounding box of the other (exact for boxes, hull extents for meshes)
+        if (keep) {
+          const float* bb = m->geom_aabb[g2];
+          creal cl[3], dd = 0; mat_tmulvec(cl, p2 + 3, t);     // centre of g1 in the frame of g2 is -R2^T t
+          for (int i = 0; i < 3; i++) { creal e = fabs(-cl[i] - (creal)bb[i]) - (creal)bb[3 + i]; if (e > 0) dd += e * e; }
           creal b = r1 + margin; keep = dd <= b * b;
         }
-        if (keep && t1 == G_BOX) {
-          creal cl[3], dd = 0; mat_tmulvec(cl, p1 + 3, t);
-          for (int i = 0; i < 3; i++) { creal e = fabs(cl[i]) - m->geom_size[g1][i]; if (e > 0) dd += e * e; }
+        if (keep) {
+          const float* bb = m->geom_aabb[g1];
+          creal cl[3], dd = 0; mat_tmulvec(cl, p1 + 3, t);      // centre of g2 in the frame of g1 is +R1^T t
+          for (int i = 0; i < 3; i++) { creal e = fabs(cl[i] - (creal)bb[i]) - (creal)bb[3 + i]; if (e > 0) dd += e * e; }
           creal b = r2 + margin; keep = dd <= b * b;
         }
       }
