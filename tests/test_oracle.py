@@ -177,6 +177,49 @@ def test_narrowphase_analytic_cases():
     assert abs(cyl[0].pos[0]) < 1e-6 and abs(cyl[0].pos[1] - 0.5) < 1e-6       # under the cylinder axis
 
 
+def test_aligned_cylinder_fast_paths_agree_with_gjk_epa():
+    """cyl_box_aligned / cyl_cyl_parallel (exact, used within 1.4 mrad of parallel) against the general GJK + EPA route on the
+    same configuration tilted by 2 mrad (just outside the fast path): distance within r*tilt, normal within the tilt."""
+    import ctypes as C
+    from oracle import mjphys
+    mjphys.build()
+    L = C.CDLL(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "libmjphys.so"))
+    dp = C.POINTER(C.c_double)
+
+    def pair(t1, p1, R1, s1, t2, p2, R2, s2, margin=0.002):
+        out = np.zeros(16 * 7); keep = [np.ascontiguousarray(x, dtype=np.float64) for x in (p1, R1.reshape(-1), s1, p2, R2.reshape(-1), s2)]
+        L.om_narrowphase_pair.restype = C.c_int
+        n = L.om_narrowphase_pair(C.c_int(t1), keep[0].ctypes.data_as(dp), keep[1].ctypes.data_as(dp), keep[2].ctypes.data_as(dp), None, C.c_int(0),
+                                  C.c_int(t2), keep[3].ctypes.data_as(dp), keep[4].ctypes.data_as(dp), keep[5].ctypes.data_as(dp), None, C.c_int(0),
+                                  C.c_double(margin), out.ctypes.data_as(dp))
+        return out[: 7 * n].reshape(n, 7)
+
+    def rot(ax, ang):
+        ax = np.asarray(ax, float) / np.linalg.norm(ax)
+        K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+        return np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+
+    CYL, BOX = 5, 6
+    box = (np.array([0, 0, 0.05]), np.eye(3), [0.1, 0.06, 0.05])
+    tilt = 2e-3
+    cases = [((0.02, 0.01, 0.1 + 0.03 - 0.001), np.eye(3)),            # cap on the top face
+             ((0.09, 0.0, 0.1 + 0.03 - 0.001), np.eye(3)),             # cap overhanging an edge
+             ((0.1 + 0.02 - 0.0005, 0.0, 0.06), np.eye(3)),            # side against a vertical face
+             ((0.0, 0.0, 0.1 + 0.02 - 0.001), rot([1, 0, 0], np.pi / 2)),   # lying on the top face
+             ((0.03, 0.01, 0.08), np.eye(3))]                          # deep inside
+    for pos, R in cases:
+        a = pair(CYL, np.array(pos), R, [0.02, 0.03, 0], BOX, *box)
+        b = pair(CYL, np.array(pos), rot([1, 0.7, 0], tilt) @ R, [0.02, 0.03, 0], BOX, *box)
+        assert len(a) == 1 and len(b) == 1
+        assert abs(a[0, 0] - b[0, 0]) < 0.03 * tilt + 2e-6 and np.abs(a[0, 4:] - b[0, 4:]).max() < 3 * tilt
+    c1 = (np.array([0.3, 0, 0.25]), np.eye(3), [0.03, 0.03, 0])
+    for pos in [(0.3, 0.0, 0.25 + 0.05 - 0.0008), (0.3 + 0.05 - 0.0005, 0, 0.25), (0.32, 0.01, 0.25 + 0.05 - 0.0008)]:
+        a = pair(CYL, *c1, CYL, np.array(pos), np.eye(3), [0.02, 0.02, 0])
+        b = pair(CYL, *c1, CYL, np.array(pos), rot([1, 0, 0], tilt), [0.02, 0.02, 0])
+        assert len(a) == 1 and len(b) == 1
+        assert abs(a[0, 0] - b[0, 0]) < 0.03 * tilt + 2e-6 and np.abs(a[0, 4:] - b[0, 4:]).max() < 3 * tilt
+
+
 def _ref_policy(task):
     import sys, types, warnings
     ref = "/root/reference/metaworld"
