@@ -51,9 +51,13 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
 
     def __init__(self, env_names, tasks_per_env, num_envs=None, seed=None, use_one_hot=False, num_tasks=None,
                  env_ids=None, max_episode_steps=None, terminate_on_success=False, task_select="random",
-                 reward_function_version="v2", device=0, engine=None, **unused):
+                 reward_function_version="v2", device=0, engine=None, recurrent_info_in_obs=False,
+                 normalize_reward_in_recurrent_info=True, reward_normalization_method=None, reward_alpha=0.001,
+                 normalize_observations=False, **unused):
         if reward_function_version != "v2":
             raise NotImplementedError("only the default v2 rewards are implemented on the device")
+        if normalize_observations:
+            raise NotImplementedError("normalize_observations relies on gymnasium.wrappers.NormalizeObservation; not provided")
         n_types = len(env_names)
         num_envs = n_types if num_envs is None else int(num_envs)
         if num_envs < n_types:
@@ -134,6 +138,14 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
         self._ep_len = np.zeros(N, dtype=np.int64)
         self._closed = False
         self._needs_reset = True
+        # optional per-sub-env wrappers of the reference that sit above the one-hot wrapper (metaworld/__init__.py:437-444)
+        from .post import StepPost
+        self.post = StepPost(N, recurrent_info_in_obs, normalize_reward_in_recurrent_info, reward_normalization_method, reward_alpha)
+        if self.post.recurrent:     # RNNBasedMetaRLWrapper's space: unbounded float32 of obs + action + reward + done (wrappers.py:55-62)
+            D = self.obs_dim + self.post.extra
+            self.obs_dtype = np.float32
+            self.single_observation_space = _gym.Box(np.full(D, -np.inf, np.float32), np.full(D, np.inf, np.float32), dtype=np.float32)
+            self.observation_space = _gym.batch_space(self.single_observation_space, num_envs)
 
     # ------------------------------------------------------------------ helpers
     def _snap(self, task: Task) -> int:
@@ -169,6 +181,8 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
         self._ep_len[:] = 0
         self._needs_reset = False
         obs = self.d_obs.cpu().numpy().astype(self.obs_dtype)
+        if self.post.active:
+            obs = self.post.on_reset(obs)
         return obs, {}
 
     def step(self, actions):
@@ -180,7 +194,6 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
         self.d_actions.copy_(self.h_actions, non_blocking=True)
         self.engine.step(self.d_actions, self.d_obs, self.d_reward, self.d_term, self.d_trunc, self.d_info,
                          self.d_final_obs, self.d_final_info, self.d_next)
-        self._maybe_rebalance()
         small = t.cat([self.d_reward[:, None], self.d_info, (self.d_term + 2 * self.d_trunc).float()[:, None]], dim=1)
         self.h_small.copy_(small, non_blocking=True)
         self.h_obs.copy_(self.d_obs, non_blocking=True)
@@ -196,9 +209,15 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
             infos["_" + k] = np.ones(self.num_envs, dtype=bool)
         self._ep_len += 1
         done = terminated | truncated
+        fo = ep_r = None
         if done.any():
             fo = self.d_final_obs.cpu().numpy().astype(self.obs_dtype)
+        if self.post.active:
+            obs, reward, fo, ep_r = self.post.on_step(obs, a, reward, terminated, truncated, final_obs=fo)
+        if done.any():
             fi = self.d_final_info.cpu().numpy()
+            if ep_r is not None:
+                fi = fi.copy(); fi[:, 7] = ep_r          # RecordEpisodeStatistics sits outside the reward normalisation
             final_obs = np.full(self.num_envs, None, dtype=object)
             for e in np.nonzero(done)[0]:
                 final_obs[e] = fo[e]
@@ -219,18 +238,14 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
             self._push_next()
         return obs, reward, terminated, truncated, infos
 
-    def _maybe_rebalance(self):
-        """Task types differ several-fold in step cost; after a few measured steps (and then rarely) the engine re-sorts
-        its CTA launch order costliest-first (mw_rebalance).  Results do not depend on the order."""
-        return   # superseded: the engine now re-sorts its launch order on the device before every step (k_order_*)
-
     def step_async(self, actions):
         self._pending_actions = actions
 
     def step_wait(self):
         return self.step(self._pending_actions)
 
-    # GPU-resident variants (no host synchronisation; task re-sampling on autoreset happens on the device)
+    # GPU-resident variants (no host synchronisation; task re-sampling on autoreset happens on the device).  They return the
+    # engine's raw outputs: the optional recurrent-obs / reward-normalisation post-processing (post.py) is a numpy-path feature.
     def enable_device_sampler(self):
         first, count = [], []
         for e, s in enumerate(self.sub):
@@ -248,7 +263,6 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
         nxt = None if getattr(self, "_device_sampler", False) else self.d_next
         self.engine.step(actions, self.d_obs, self.d_reward, self.d_term, self.d_trunc, self.d_info, self.d_final_obs,
                          self.d_final_info, nxt)
-        self._maybe_rebalance()
         return self.d_obs, self.d_reward, self.d_term, self.d_trunc, self.d_info
 
     # attribute RPC used by metaworld/evaluation.py:48-169 and the reference tests

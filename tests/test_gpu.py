@@ -289,3 +289,33 @@ def test_evaluation_loop_on_device_envs(torch_cuda):
     assert set(per_task) == set(env.get_attr("task_name")) and len(per_task) == 10
     assert all(len(v) == 2 for v in rets.values()) and 0.0 <= sr <= 1.0 and np.isfinite(ret)
     assert ag.resets >= 20 + 2 * 10 and not any(env.get_attr("terminate_on_success"))
+
+
+def test_recurrent_obs_and_reward_normalisation(torch_cuda):
+    """RNNBasedMetaRLWrapper / NormalizeRewardsExponential semantics on the vector env (metaworld/__init__.py:437-444)."""
+    from metaworld_b200.vector_env import make_mt_envs
+    plain = make_mt_envs("MT10", seed=3, num_envs=10, max_episode_steps=6, use_one_hot=True)
+    rec = make_mt_envs("MT10", seed=3, num_envs=10, max_episode_steps=6, use_one_hot=True, recurrent_info_in_obs=True,
+                       reward_normalization_method="exponential", reward_alpha=0.1)
+    o0, _ = plain.reset(); o1, _ = rec.reset()
+    assert o1.shape == (10, 49 + 6) and rec.single_observation_space.shape == (55,) and np.array_equal(o1[:, :49], o0) and not o1[:, 49:].any()
+    rng = np.random.default_rng(0)
+    mean, var, epr = np.zeros(10), np.ones(10), np.zeros(10)
+    for t in range(13):
+        a = rng.uniform(-1, 1, size=(10, 4)).astype(np.float32)
+        po, pr, pt, ptr, pi = plain.step(a)
+        ro, rr, rt, rtr, ri = rec.step(a)
+        done = pt | ptr
+        assert np.array_equal(done, rt | rtr) and np.array_equal(ro[:, :49], po)
+        for _ in range(2):
+            mean = 0.9 * mean + 0.1 * pr; var = 0.9 * var + 0.1 * np.square(pr - mean)
+        exp_r = pr / (np.sqrt(var) + 1e-8)
+        assert np.allclose(rr, exp_r, atol=1e-9)
+        epr += exp_r
+        live = ~done
+        assert np.allclose(ro[live, 49:53], a[live]) and np.allclose(ro[live, 53], pr[live] / 10.0, atol=1e-6) and not ro[live, 54].any()
+        if done.any():
+            assert not ro[done, 49:].any()
+            assert np.allclose(np.stack(ri["final_obs"][done])[:, 53], pr[done] / 10.0, atol=1e-6)
+            assert np.allclose(ri["final_info"]["episode"]["r"][done], epr[done], atol=1e-6)
+            epr[done] = 0

@@ -1,0 +1,61 @@
+"""metaworld_b200.post.StepPost against scalar transcriptions of the reference wrappers it vectorises
+(metaworld/wrappers.py:35-88 RNNBasedMetaRLWrapper, :233-258 NormalizeRewardsExponential; stacking order and
+RecordEpisodeStatistics placement from metaworld/__init__.py:437-446)."""
+import numpy as np
+
+from metaworld_b200.post import StepPost
+
+
+class ScalarStack:
+    """one sub-env's wrapper stack, written the way the reference applies it to a single env"""
+
+    def __init__(self, recurrent, norm_in_obs, exponential, alpha):
+        self.recurrent, self.norm_in_obs, self.exponential, self.alpha = recurrent, norm_in_obs, exponential, alpha
+        self.mean, self.var, self.ep_ret = 0.0, 1.0, 0.0
+
+    def reset(self, obs):
+        self.ep_ret = 0.0
+        return np.concatenate([obs, np.zeros(4), [0.0], [0.0]]) if self.recurrent else obs
+
+    def _upd(self, r):
+        self.mean = (1 - self.alpha) * self.mean + self.alpha * r
+        self.var = (1 - self.alpha) * self.var + self.alpha * np.square(r - self.mean)
+
+    def step(self, next_obs, action, reward, term, trunc):
+        o = next_obs
+        if self.recurrent:
+            o = np.concatenate([next_obs, action, [float(reward) / 10.0 if self.norm_in_obs else float(reward)], [float(term or trunc)]])
+        r = reward
+        if self.exponential:
+            self._upd(reward)          # step(): explicit update ...
+            self._upd(reward)          # ... and a second one inside _apply_normalize_reward
+            r = reward / (np.sqrt(self.var) + 1e-8)
+        self.ep_ret += r
+        return o, r
+
+
+def test_steppost_matches_scalar_wrappers():
+    rng = np.random.default_rng(0)
+    N, D = 6, 49
+    for recurrent, norm_in_obs, expo in [(True, True, True), (True, False, False), (False, True, True), (False, False, False)]:
+        post = StepPost(N, recurrent, norm_in_obs, "exponential" if expo else None, reward_alpha=0.05)
+        stacks = [ScalarStack(recurrent, norm_in_obs, expo, 0.05) for _ in range(N)]
+        obs0 = rng.normal(size=(N, D))
+        out = post.on_reset(obs0)
+        ref = np.stack([s.reset(obs0[i]) for i, s in enumerate(stacks)])
+        assert np.array_equal(out, ref)
+        for t in range(40):
+            term_obs, reset_obs = rng.normal(size=(N, D)), rng.normal(size=(N, D))
+            act, rew = rng.uniform(-1, 1, size=(N, 4)), rng.normal(size=N) * 3
+            term, trunc = rng.random(N) < 0.1, rng.random(N) < 0.1
+            done = term | trunc
+            obs_in = np.where(done[:, None], reset_obs, term_obs)                       # SAME_STEP autoreset: obs is the reset obs
+            o, r, fo, fin = post.on_step(obs_in, act, rew, term, trunc, final_obs=term_obs)
+            for i, s in enumerate(stacks):
+                so, sr = s.step(term_obs[i], act[i], rew[i], term[i], trunc[i])
+                assert np.isclose(r[i], sr, rtol=0, atol=1e-12)
+                if done[i]:
+                    assert np.allclose(fo[i], so) and np.isclose(fin[i], s.ep_ret)
+                    assert np.allclose(o[i], s.reset(reset_obs[i]))
+                else:
+                    assert np.allclose(o[i], so) and fin[i] == 0.0
