@@ -800,10 +800,16 @@ __device__ __noinline__ void mw_solve(const MwModel* __restrict__ m, WarpScratch
 
 // ------------------------------------------------------------------ forward dynamics + Euler
 // mj_forward  (positions -> qacc); leaves link poses / contacts / efc forces in the scratch.
+// PHASE_SYNC: the step kernel is far larger than the instruction cache, and with warps of one CTA spread over different phases
+// most issue slots are lost to instruction fetch (ncu: stall_no_inst 55-60 %).  All warps of a CTA run the same model and make
+// the same number of forward passes, so a CTA barrier at every phase boundary is legal; it keeps the CTA's warps inside the
+// same code region and lets them share the fetched lines.  (Warps that have exited are not counted by the barrier.)
+#define PHASE_SYNC() __syncthreads()
 __device__ __noinline__ void mw_forward(const MwModel* __restrict__ m, const float* __restrict__ meshvert, WarpScratch* w, int lane) {
   const int nv = m->nv;
+  PHASE_SYNC();
   long long t0 = clock64(), t1;
-#define PROF_(i) { t1 = clock64(); if (lane == 0) w->prof[i] += t1 - t0; t0 = t1; }
+#define PROF_(i) { t1 = clock64(); if (lane == 0) w->prof[i] += t1 - t0; t0 = t1; PHASE_SYNC(); }
   mw_kinematics(m, w, lane);
   LaneDof L; mw_lane_dof(m, w, lane, &L);
   mw_mass_matrix(m, w, L, lane);
