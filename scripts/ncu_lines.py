@@ -4,6 +4,7 @@ import csv, re, sys, os, collections
 path = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 rows = csv.reader(open(path, newline=''))
 cur_file = None; hdr = None; per_line = collections.Counter(); per_line_inst = collections.Counter(); text = {}
+stalls = collections.Counter()
 cur_line = None
 for r in rows:
     if not r: continue
@@ -14,10 +15,15 @@ for r in rows:
         cur_line = (cur_file, int(r[0])); text[cur_line] = r[1].strip(); continue
     try:
         per_line[cur_line] += int(r[iS]); per_line_inst[cur_line] += int(r[iI])
+        for i, h in enumerate(hdr):
+            if h.startswith("stall_") and "Not Issued" not in h: stalls[h] += int(r[i])
     except (ValueError, IndexError):
         pass
 tot_s = sum(per_line.values()); tot_i = sum(per_line_inst.values())
 print(f"total samples {tot_s}  warp instructions {tot_i}")
+ts = max(1, sum(stalls.values()))
+print("\n== warp stall reasons (all samples)")
+for k, v in stalls.most_common(10): print(f"  {100*v/ts:5.1f}%  {k}")
 defs = collections.defaultdict(list)
 src_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "metaworld_b200", "csrc")
 for f in set(k[0] for k in per_line):
