@@ -172,3 +172,22 @@ def test_two_rank_gather_gloo(tmp_path):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29533", str(script), ROOT], capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0 and "GLOO_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_task_registry_matches_oracle_classes():
+    """The device's per-task constants (metaworld_b200/tasks.py, fed to the kernels through MwTaskConst) and the oracle's
+    task classes (oracle/tasks.py) are two independent transcriptions of the 50 reference constructors: they must agree on
+    the model file, hand / mocap workspace, initial hand position, reset space and goal space."""
+    from metaworld_b200.tasks import TASKS
+    from metaworld_b200 import benchmarks as B
+    from oracle.tasks import TASKS as OT
+    assert set(TASKS) == set(OT) == set(B.ALL_V3) and len(TASKS) == 50
+    assert sorted(t.task_id for t in TASKS.values()) == list(range(50))
+    for name, spec in TASKS.items():
+        env = OT[name]()
+        assert env.xml == spec.xml, name
+        assert np.allclose(env.mocap_low, spec.hand_low) and np.allclose(env.mocap_high, spec.hand_high), name
+        assert np.allclose(env.hand_init_pos, spec.hand_init_pos), name
+        lo, hi = env.random_reset_space()
+        assert np.allclose(lo, spec.rand_low) and np.allclose(hi, spec.rand_high), name
+        assert np.allclose(env.goal_low, spec.goal_low) and np.allclose(env.goal_high, spec.goal_high), name
