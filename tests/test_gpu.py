@@ -319,3 +319,28 @@ def test_recurrent_obs_and_reward_normalisation(torch_cuda):
             assert np.allclose(np.stack(ri["final_obs"][done])[:, 53], pr[done] / 10.0, atol=1e-6)
             assert np.allclose(ri["final_info"]["episode"]["r"][done], epr[done], atol=1e-6)
             epr[done] = 0
+
+
+def test_metalearning_evaluation_on_device_envs(torch_cuda):
+    """metalearning_evaluation (metaworld/evaluation.py:108-169) over real ML10 test envs: exercises sample_tasks,
+    toggle_sample_tasks_on_reset and the adaptation / evaluation alternation end to end."""
+    from metaworld_b200.vector_env import make_ml_envs
+    from metaworld_b200 import evaluation as E
+
+    class Agent:
+        def __init__(self): self.rng = np.random.default_rng(1); self.inits = self.adapts = self.steps = 0
+        def init(self): self.inits += 1
+        def eval_action(self, obs): return self.rng.uniform(-1, 1, size=(len(obs), 4)).astype(np.float32)
+        def adapt_action(self, obs): return self.eval_action(obs), {"logp": np.zeros(len(obs))}
+        def reset(self, mask): pass
+        def step(self, ts): self.steps += 1; assert ts.observation.shape == (20, 39) and ts.reward.shape == (20,)
+        def adapt(self): self.adapts += 1
+
+    env = make_ml_envs("ML10", seed=7, meta_batch_size=20, split="test", max_episode_steps=8)
+    assert env.num_envs == 20 and env.get_attr("_partially_observable") is not None
+    ag = Agent()
+    sr, ret, per_task = E.metalearning_evaluation(ag, env, num_evals=2, adaptation_steps=1, adaptation_episodes=2, evaluation_episodes=1)
+    assert ag.inits == 2 and ag.adapts == 2 and ag.steps >= 2 * 2 * 8
+    assert set(per_task) == set(env.get_attr("task_name")) and len(per_task) == 5 and 0.0 <= sr <= 1.0 and np.isfinite(ret)
+    o, _ = env.reset()
+    assert not o[:, 36:39].any()          # meta-learning envs are partially observable: goal zeroed
