@@ -2,7 +2,7 @@
 //
 // One warp = one environment for a whole env step: 5 x (forward dynamics + semi-implicit Euler), one more
 // forward pass, observation, reward/info, time-limit / success termination and SAME_STEP autoreset, with the
-// per-env state making a single 512-byte round trip to HBM (coalesced 128-bit loads/stores).  One CTA = 8 warps
+// per-env state making a single 512-byte round trip to HBM (coalesced 128-bit loads/stores).  One CTA = WARPS_PER_BLOCK warps
 // that share one task model; the ~10 KB model blob is staged into shared memory with a TMA bulk copy
 // (cp.async.bulk + mbarrier).  There is no CPU fallback: every entry point launches CUDA kernels or fails.
 #include <cuda_runtime.h>
