@@ -264,3 +264,134 @@ def test_reference_scripted_policy_succeeds_on_oracle(task):
                 wins += 1
                 break
     assert wins >= 4, f"{task}: scripted policy solved {wins}/5 goals on the oracle"
+
+
+def _vee(S):
+    return np.array([S[2, 1] - S[1, 2], S[0, 2] - S[2, 0], S[1, 0] - S[0, 1]]) / 2
+
+
+def test_mass_matrix_equals_finite_difference_kinetic_energy():
+    """qM against an independent construction: kinetic energy of every body from finite-differenced inertial-frame poses
+    (door-open: hinge / slide joints only, so qpos can be perturbed directly)."""
+    from oracle.tasks import TASKS
+    from oracle import mjphys as P
+    env = TASKS["door-open-v3"]()
+    env.set_task_vec(np.array([0.05, 0.9, 0.15]), False)
+    env.reset()
+    rng = np.random.default_rng(0)
+    q0 = np.array(env.data.qpos).copy()
+    q0[:9] += rng.normal(size=9) * 0.2
+    env.data.qpos = q0
+    P.mj_forward(env.model, env.data)
+    nv = len(env.data.qvel)
+    M = np.array(env.data.qM).reshape(nv, nv)
+    assert np.allclose(M, M.T, atol=1e-12) and np.linalg.eigvalsh(M).min() > 0
+    from metaworld_b200 import modelzoo
+    arr = modelzoo.full_model(env.xml).arrays
+    mass = np.array(arr["body_mass"]); inertia = np.array(arr["body_inertia"]).reshape(-1, 3); armature = np.array(arr["dof_armature"])
+    x0 = np.array(env.data.xipos).reshape(-1, 3).copy(); R0 = np.array(env.data.ximat).reshape(-1, 3, 3).copy()
+    eps = 1e-6
+    for _ in range(4):
+        v = rng.normal(size=nv)
+        env.data.qpos = q0 + eps * v
+        P.mj_forward(env.model, env.data)
+        x1 = np.array(env.data.xipos).reshape(-1, 3); R1 = np.array(env.data.ximat).reshape(-1, 3, 3)
+        ke = 0.0
+        for b in range(len(mass)):
+            vc = (x1[b] - x0[b]) / eps
+            w_world = _vee((R1[b] - R0[b]) @ R0[b].T) / eps
+            w_body = R0[b].T @ w_world
+            ke += 0.5 * mass[b] * vc @ vc + 0.5 * w_body @ (inertia[b] * w_body)
+        ke += 0.5 * np.sum(armature * v * v)          # rotor inertia is part of qM but not of the bodies' motion
+        assert abs(0.5 * v @ M @ v - ke) < 2e-5 * max(1.0, ke)
+
+
+def test_constraint_solution_satisfies_dynamics_and_friction_cones():
+    """At contact-rich states of the policy goldens: M qacc = qfrc_smooth + J^T f exactly (the solver's stationarity), contact
+    normal forces are non-negative and friction stays inside the elliptic cone."""
+    from oracle.tasks import TASKS
+    from oracle import mjphys as P
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    checked = 0
+    for task in ("pick-place-v3", "box-close-v3", "peg-insert-side-v3", "button-press-v3"):
+        g = np.load(os.path.join(gold, f"traj_{task}.npz"))
+        env = TASKS[task]()
+        n = len(env.random_reset_space()[0])
+        env.set_task_vec(g["p_rand_vec"][0][:n], False); env.reset()
+        for t in range(20, g["p_qpos"].shape[1], 12):
+            env.data.qpos = g["p_qpos"][0, t]; env.data.qvel = g["p_qvel"][0, t]; env.data.mocap_pos[0][:] = g["p_mocap"][0, t]
+            a = g["p_actions"][0, t]; env.data.ctrl = (float(a[3]), -float(a[3]))
+            P.mj_forward(env.model, env.data)
+            nv, nefc = len(env.data.qvel), env.data.nefc
+            M = np.array(env.data.qM).reshape(nv, nv)
+            J = np.array(env.data.efc_J)[: nefc * nv].reshape(nefc, nv)
+            f = np.array(env.data.efc_force)[:nefc]
+            res = M @ np.array(env.data.qacc) - np.array(env.data.qfrc_smooth) - J.T @ f
+            scale = max(1.0, np.abs(np.array(env.data.qfrc_smooth)).max(), np.abs(J.T @ f).max())
+            assert np.abs(res).max() < 1e-6 * scale, (task, t, np.abs(res).max(), scale)
+            for c in env.data.contact:
+                if c.efc_address < 0:
+                    continue
+                fn = f[c.efc_address]
+                assert fn >= -1e-9
+                ft = f[c.efc_address + 1: c.efc_address + c.dim]
+                fr = np.array(c.friction)[[0, 1, 2][: c.dim - 1]] if c.dim > 1 else np.zeros(0)
+                if c.dim > 1 and fn > 0:
+                    assert np.sqrt(np.sum((ft / np.maximum(fr, 1e-12)) ** 2)) <= fn * (1 + 1e-6) + 1e-9
+                checked += 1
+    assert checked > 50
+
+
+def test_gravity_bias_equals_potential_gradient():
+    """With qvel = 0 the bias force must be the gradient of the gravitational potential sum_b m_b g z_b (finite differences)."""
+    from oracle.tasks import TASKS
+    from oracle import mjphys as P
+    from metaworld_b200 import modelzoo
+    env = TASKS["drawer-open-v3"]()
+    env.set_task_vec(np.array([0.0, 0.9, 0.0]), False); env.reset()
+    mass = np.array(modelzoo.full_model(env.xml).arrays["body_mass"])
+    rng = np.random.default_rng(1)
+    q0 = np.array(env.data.qpos).copy(); q0[:9] += rng.normal(size=9) * 0.15
+    nv = len(env.data.qvel)
+
+    def potential(q):
+        env.data.qpos = q; env.data.qvel = np.zeros(nv)
+        P.mj_forward(env.model, env.data)
+        return 9.81 * float(mass @ np.array(env.data.xipos).reshape(-1, 3)[:, 2])
+
+    eps = 1e-6
+    grad = np.array([(potential(q0 + eps * np.eye(nv)[i]) - potential(q0 - eps * np.eye(nv)[i])) / (2 * eps) for i in range(nv)])
+    potential(q0)
+    assert np.abs(np.array(env.data.qfrc_bias) - grad).max() < 1e-5 * max(1.0, np.abs(grad).max())
+
+
+def test_contact_jacobian_is_the_rate_of_change_of_distance():
+    """For every active contact: (J qvel)[normal row] = d(dist)/dt under the motion qvel, by finite differences on qpos
+    (hinge / slide model); checks the contact frame orientation, the sign convention and the point Jacobians together."""
+    from oracle.tasks import TASKS
+    from oracle import mjphys as P
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    task = "button-press-topdown-v3"
+    g = np.load(os.path.join(gold, f"traj_{task}.npz"))
+    env = TASKS[task]()
+    env.set_task_vec(g["p_rand_vec"][0][:3], False); env.reset()
+    rng = np.random.default_rng(2)
+    checked = 0
+    for t in range(30, g["p_qpos"].shape[1], 10):
+        q0 = g["p_qpos"][0, t].copy()
+        env.data.qpos = q0; env.data.mocap_pos[0][:] = g["p_mocap"][0, t]
+        P.mj_forward(env.model, env.data)
+        nv, nefc = len(env.data.qvel), env.data.nefc
+        J = np.array(env.data.efc_J)[: nefc * nv].reshape(nefc, nv).copy()
+        base = {(c.geom1, c.geom2, tuple(np.round(c.pos, 4))): (c.dist, c.efc_address) for c in env.data.contact if c.efc_address >= 0}
+        v = rng.normal(size=nv) * 0.5
+        eps = 1e-7
+        env.data.qpos = q0 + eps * v
+        P.mj_forward(env.model, env.data)
+        for c in env.data.contact:
+            key = (c.geom1, c.geom2, tuple(np.round(c.pos, 4)))
+            if key in base:
+                d0, row = base[key]
+                assert abs((c.dist - d0) / eps - J[row] @ v) < 2e-3 * max(1.0, np.abs(J[row]).sum()), (t, key)
+                checked += 1
+    assert checked >= 10
