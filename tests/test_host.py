@@ -191,3 +191,18 @@ def test_task_registry_matches_oracle_classes():
         lo, hi = env.random_reset_space()
         assert np.allclose(lo, spec.rand_low) and np.allclose(hi, spec.rand_high), name
         assert np.allclose(env.goal_low, spec.goal_low) and np.allclose(env.goal_high, spec.goal_high), name
+
+
+def test_bench_helpers():
+    """bench.py host-side helpers: usable core count respects the cgroup quota; algorithmic bytes follow SURVEY 8(d)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    n = bench.usable_cores()
+    assert 1 <= n <= (os.cpu_count() or 1)
+    names, total = bench.implemented_tasks("MT50")
+    assert len(names) == total == 50
+    b = bench.algorithmic_bytes(["reach-v3"])
+    assert b == 4 * (2 * 16 + 4 * 15 + 120)          # nq 16, nv 15 -> 848 B per env step
+    assert abs(bench.algorithmic_bytes(names) - 792.32) < 0.5
