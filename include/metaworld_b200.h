@@ -76,7 +76,8 @@ int mw_set_options(mw_engine*, int max_episode_steps, int terminate_on_success, 
 /* per-env contiguous range of snapshot ids [first, first+count) used by the device-side task sampler */
 int mw_set_goal_sets(mw_engine*, const int* first /*host [n_envs]*/, const int* count /*host [n_envs]*/);
 
-/* raw state access (tests, checkpoint/resume incl. physics state): n_envs * 512 bytes */
+/* raw state access (tests, checkpoint/resume incl. physics state): n_envs * 512 bytes; record = qpos[18] float64, then
+ * float32: qvel[17], warm-start qacc[17], mocap_pos[3], prev_obs[18], ... (metaworld_b200/engine.py: ENVSTATE_DTYPE) */
 int mw_get_state(mw_engine*, void* out_host);
 int mw_set_state(mw_engine*, const void* in_host);
 /* debug: run nstep raw physics substeps (mj_step) on every env with fixed ctrl, no reward/obs */

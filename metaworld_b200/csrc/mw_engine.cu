@@ -86,7 +86,7 @@ DEV void load_env(WarpShared* ws, const MwEnvState* src, int lane) {
   ((float4*)&ws->es)[lane] = ((const float4*)src)[lane];     // 32 lanes x 16 B = the whole 512 B record
   SYNCW();
   WarpScratch* w = &ws->w;
-  if (lane < MW_MAXNQ) w->qpos[lane] = ws->es.qpos[lane];
+  if (lane < MW_MAXNQ) { w->qposd[lane] = ws->es.qpos[lane]; w->qpos[lane] = (real)w->qposd[lane]; }
   if (lane < MW_MAXDOF) { w->qvel[lane] = ws->es.qvel[lane]; w->warm[lane] = ws->es.warm[lane]; }
   if (lane < 3) { w->mocap_pos[lane] = ws->es.mocap_pos[lane]; w->shift[lane] = ws->es.shift[lane]; }
   if (lane == 0) { w->mocap_quat[0] = 1; w->mocap_quat[1] = 0; w->mocap_quat[2] = 1; w->mocap_quat[3] = 0; w->ctrl[0] = w->ctrl[1] = 0; }
@@ -94,7 +94,7 @@ DEV void load_env(WarpShared* ws, const MwEnvState* src, int lane) {
 }
 DEV void store_env(WarpShared* ws, MwEnvState* dst, int lane) {
   WarpScratch* w = &ws->w;
-  if (lane < MW_MAXNQ) ws->es.qpos[lane] = (float)w->qpos[lane];
+  if (lane < MW_MAXNQ) ws->es.qpos[lane] = w->qposd[lane];
   if (lane < MW_MAXDOF) { ws->es.qvel[lane] = (float)w->qvel[lane]; ws->es.warm[lane] = (float)w->warm[lane]; }
   if (lane < 3) { ws->es.mocap_pos[lane] = (float)w->mocap_pos[lane]; ws->es.shift[lane] = (float)w->shift[lane]; }
   SYNCW();
@@ -237,7 +237,7 @@ k_snapshot(EngineDev e, const int* __restrict__ block_model, const int* __restri
   for (int pass = 0; pass < 2; pass++) {
     if (pass == 1 || true) {
       // mj_resetData (pass 0: a freshly constructed env is in the same state)
-      if (lane < MW_MAXNQ) w->qpos[lane] = lane < m->nq ? (real)m->qpos0[lane] : (real)0;
+      if (lane < MW_MAXNQ) QSET(w, lane, lane < m->nq ? m->qpos0d[lane] : 0.0);
       if (lane < MW_MAXDOF) { w->qvel[lane] = 0; w->warm[lane] = 0; }
       if (lane < 3) w->mocap_pos[lane] = m->mocap_pos0[lane];
       if (lane < 4) w->mocap_quat[lane] = m->mocap_quat0[lane];

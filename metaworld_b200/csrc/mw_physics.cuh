@@ -38,6 +38,9 @@ struct WarpScratch {
   real lpos[MW_MAXLINK][3], lquat[MW_MAXLINK][4], lmat[MW_MAXLINK][9];
   real daxis[MW_MAXDOF][3], danchor[MW_MAXDOF][3];
   real qpos[MW_MAXNQ], qvel[MW_MAXDOF], warm[MW_MAXDOF];
+  // positions are carried in float64 (state record, kinematic chain, collision inputs): float32 storage of qpos was the
+  // largest per-step noise source (6e-8 relative, every step); qpos[] above is the float copy the dynamics reads
+  double qposd[MW_MAXNQ], lposd[MW_MAXLINK][3], lquatd[MW_MAXLINK][4];
   real ctrl[2], mocap_pos[3], mocap_quat[4], shift[3];
   real qfrc_smooth[MW_MAXDOF], qacc_smooth[MW_MAXDOF], qfrc_con[MW_MAXDOF], qacc[MW_MAXDOF];
   real vMa[MW_MAXDOF], vSearch[MW_MAXDOF], vMs[MW_MAXDOF], vTmp[MW_MAXDOF];
@@ -52,6 +55,7 @@ struct WarpScratch {
 };
 
 #define SYNCW() __syncwarp()
+#define QSET(w, i, v) { (w)->qposd[i] = (double)(v); (w)->qpos[i] = (real)(w)->qposd[i]; }   /* write a generalized position */
 
 // ------------------------------------------------------------------ kinematics  [MuJoCo mj_kinematics]
 // Sequential over the (short) link chain; every lane computes the same values, lane 0 stores.
@@ -59,44 +63,44 @@ __device__ __noinline__ void mw_kinematics(const MwModel* __restrict__ m, WarpSc
   const int nl = m->nlink;
   for (int l = 0; l < nl; l++) {
     int p = m->link_parent[l];
-    real pos[3], quat[4], R[9];
+    double pos[3], quat[4], R[9];
     if (p < 0) {
-      if (m->link_shift[l]) { for (int i = 0; i < 3; i++) pos[i] = m->link_pos[l][i] + w->shift[i]; }
+      if (m->link_shift[l]) { for (int i = 0; i < 3; i++) pos[i] = (double)m->link_pos[l][i] + (double)w->shift[i]; }
       else { for (int i = 0; i < 3; i++) pos[i] = m->link_pos[l][i]; }
       for (int i = 0; i < 4; i++) quat[i] = m->link_quat[l][i];
     } else {
-      real lp[3] = {m->link_pos[l][0], m->link_pos[l][1], m->link_pos[l][2]};
-      real lq[4] = {m->link_quat[l][0], m->link_quat[l][1], m->link_quat[l][2], m->link_quat[l][3]};
-      real t[3]; mat_mulvec(t, w->lmat[p], lp); v3add(pos, w->lpos[p], t);
-      quat_mul(quat, w->lquat[p], lq);
+      double lp[3] = {m->link_pos[l][0], m->link_pos[l][1], m->link_pos[l][2]};
+      double lq[4] = {m->link_quat[l][0], m->link_quat[l][1], m->link_quat[l][2], m->link_quat[l][3]};
+      double Rp[9], t[3]; quat2mat(Rp, w->lquatd[p]); mat_mulvec(t, Rp, lp); v3add(pos, w->lposd[p], t);
+      quat_mul(quat, w->lquatd[p], lq);
     }
     const int jt = m->link_jtype[l], qa = m->link_qadr[l], da = m->link_dadr[l];
     if (jt == JT_FREE) {
-      real q[4] = {w->qpos[qa + 3], w->qpos[qa + 4], w->qpos[qa + 5], w->qpos[qa + 6]};
+      double q[4] = {w->qposd[qa + 3], w->qposd[qa + 4], w->qposd[qa + 5], w->qposd[qa + 6]};
       quat_normalize(q);
-      for (int i = 0; i < 3; i++) pos[i] = w->qpos[qa + i];
+      for (int i = 0; i < 3; i++) pos[i] = w->qposd[qa + i];
       for (int i = 0; i < 4; i++) quat[i] = q[i];
       quat2mat(R, quat);
       if (lane == 0) {
-        for (int i = 0; i < 4; i++) w->qpos[qa + 3 + i] = q[i];
+        for (int i = 0; i < 4; i++) QSET(w, qa + 3 + i, q[i]);
         for (int i = 0; i < 3; i++) {
-          for (int k = 0; k < 3; k++) { w->daxis[da + i][k] = (i == k); w->danchor[da + i][k] = pos[k]; }
-          w->daxis[da + 3 + i][0] = R[i]; w->daxis[da + 3 + i][1] = R[3 + i]; w->daxis[da + 3 + i][2] = R[6 + i];
-          for (int k = 0; k < 3; k++) w->danchor[da + 3 + i][k] = pos[k];
+          for (int k = 0; k < 3; k++) { w->daxis[da + i][k] = (i == k); w->danchor[da + i][k] = (real)pos[k]; }
+          w->daxis[da + 3 + i][0] = (real)R[i]; w->daxis[da + 3 + i][1] = (real)R[3 + i]; w->daxis[da + 3 + i][2] = (real)R[6 + i];
+          for (int k = 0; k < 3; k++) w->danchor[da + 3 + i][k] = (real)pos[k];
         }
       }
     } else {
-      real jax[3] = {m->link_jaxis[l][0], m->link_jaxis[l][1], m->link_jaxis[l][2]};
-      real jp[3] = {m->link_jpos[l][0], m->link_jpos[l][1], m->link_jpos[l][2]};
-      real axis[3], anchor[3], t[3];
+      double jax[3] = {m->link_jaxis[l][0], m->link_jaxis[l][1], m->link_jaxis[l][2]};
+      double jp[3] = {m->link_jpos[l][0], m->link_jpos[l][1], m->link_jpos[l][2]};
+      double axis[3], anchor[3], t[3];
       quat_normalize(quat);
       quat2mat(R, quat);
       mat_mulvec(axis, R, jax);
       mat_mulvec(t, R, jp); v3add(anchor, pos, t);
-      real q = w->qpos[qa] - (real)m->qpos0[qa];
+      double q = w->qposd[qa] - m->qpos0d[qa];
       if (jt == JT_SLIDE) v3addscl(pos, pos, axis, q);
       else {
-        real qr[4], qn[4];
+        double qr[4], qn[4];
         quat_axisangle(qr, jax, q);
         quat_mul(qn, quat, qr);
         for (int i = 0; i < 4; i++) quat[i] = qn[i];
@@ -104,14 +108,14 @@ __device__ __noinline__ void mw_kinematics(const MwModel* __restrict__ m, WarpSc
         quat2mat(R, quat);
         mat_mulvec(t, R, jp); v3sub(pos, anchor, t);
       }
-      if (lane == 0) for (int k = 0; k < 3; k++) { w->daxis[da][k] = axis[k]; w->danchor[da][k] = anchor[k]; }
+      if (lane == 0) for (int k = 0; k < 3; k++) { w->daxis[da][k] = (real)axis[k]; w->danchor[da][k] = (real)anchor[k]; }
     }
     quat_normalize(quat);
     quat2mat(R, quat);
     if (lane == 0) {
-      for (int i = 0; i < 3; i++) w->lpos[l][i] = pos[i];
-      for (int i = 0; i < 4; i++) w->lquat[l][i] = quat[i];
-      for (int i = 0; i < 9; i++) w->lmat[l][i] = R[i];
+      for (int i = 0; i < 3; i++) { w->lposd[l][i] = pos[i]; w->lpos[l][i] = (real)pos[i]; }
+      for (int i = 0; i < 4; i++) { w->lquatd[l][i] = quat[i]; w->lquat[l][i] = (real)quat[i]; }
+      for (int i = 0; i < 9; i++) w->lmat[l][i] = (real)R[i];
     }
     SYNCW();
   }
@@ -349,8 +353,8 @@ __device__ __noinline__ void mw_collide(const MwModel* __restrict__ m, const flo
       for (int i = 0; i < 9; i++) Rw[i] = Rl[i];
     } else {
       creal Lm[9], Lp[3], t[3];
-      for (int i = 0; i < 9; i++) Lm[i] = w->lmat[l][i];
-      for (int i = 0; i < 3; i++) Lp[i] = w->lpos[l][i];
+      quat2mat(Lm, w->lquatd[l]);
+      for (int i = 0; i < 3; i++) Lp[i] = w->lposd[l][i];
       mat_mulvec(t, Lm, gp); v3add(pos, Lp, t);
       mat_mul(Rw, Lm, Rl);
     }
@@ -857,20 +861,21 @@ __device__ __noinline__ void mw_euler(const MwModel* __restrict__ m, WarpScratch
   real acc = mw_chol_solve(w->H, rhs, nv, lane);
   if (lane < nv) { w->qvel[lane] += h * acc; w->warm[lane] = w->qacc[lane]; }
   SYNCW();
-  // positions
+  // positions (float64 state; the float copy is refreshed for the dynamics)
   if (lane < m->nlink) {
     int l = lane, jt = m->link_jtype[l], qa = m->link_qadr[l], da = m->link_dadr[l];
+    const double hd = (double)h;
     if (jt == JT_FREE) {
-      for (int i = 0; i < 3; i++) w->qpos[qa + i] += h * w->qvel[da + i];
-      real wv[3] = {w->qvel[da + 3], w->qvel[da + 4], w->qvel[da + 5]};
-      real n = v3norm(wv);
-      if (n >= MW_EPS) {
-        real ax[3] = {wv[0] / n, wv[1] / n, wv[2] / n}, dq[4], q[4] = {w->qpos[qa + 3], w->qpos[qa + 4], w->qpos[qa + 5], w->qpos[qa + 6]}, r[4];
-        quat_axisangle(dq, ax, n * h);
+      for (int i = 0; i < 3; i++) QSET(w, qa + i, w->qposd[qa + i] + hd * (double)w->qvel[da + i]);
+      double wv[3] = {w->qvel[da + 3], w->qvel[da + 4], w->qvel[da + 5]};
+      double n = v3norm(wv);
+      if (n >= (double)MW_EPS) {
+        double ax[3] = {wv[0] / n, wv[1] / n, wv[2] / n}, dq[4], q[4] = {w->qposd[qa + 3], w->qposd[qa + 4], w->qposd[qa + 5], w->qposd[qa + 6]}, r[4];
+        quat_axisangle(dq, ax, n * hd);
         quat_mul(r, q, dq); quat_normalize(r);
-        for (int i = 0; i < 4; i++) w->qpos[qa + 3 + i] = r[i];
+        for (int i = 0; i < 4; i++) QSET(w, qa + 3 + i, r[i]);
       }
-    } else w->qpos[qa] += h * w->qvel[da];
+    } else QSET(w, qa, w->qposd[qa] + hd * (double)w->qvel[da]);
   }
   SYNCW();
 }

@@ -10,7 +10,7 @@
 
 // persistent per-environment record (128 floats = 512 B, one coalesced warp load/store)
 struct MwEnvState {
-  float qpos[MW_MAXNQ];      // 18
+  double qpos[MW_MAXNQ];     // 18 (float64: 36 words; positions carry no per-step float32 rounding)
   float qvel[MW_MAXDOF];     // 17
   float warm[MW_MAXDOF];     // 17
   float mocap_pos[3];
@@ -24,7 +24,7 @@ struct MwEnvState {
   float partially_observable;
   float snapshot;            // snapshot slot this episode started from
   float episode;             // episodes completed (drives the device-side task sampler)
-  float ep_return, pad[22];
+  float ep_return, pad[4];
 };
 static_assert(sizeof(MwEnvState) == 128 * 4, "MwEnvState must be 128 floats");
 

@@ -11,7 +11,7 @@ __device__ void eng_sim(const TaskCtx& c, int nstep, int lane);
 // ---------------------------------------------------------------- helpers shared by task families
 // `_set_obj_xyz` (sawyer_xyz_env.py:351-361): qpos[9:12] = pos, qvel[9:15] = 0, set_state -> mj_forward
 DEV void set_obj_xyz(const TaskCtx& c, const real* pos, int lane) {
-  if (lane == 0) { for (int i = 0; i < 3; i++) c.w->qpos[9 + i] = pos[i]; for (int i = 9; i < 15; i++) c.w->qvel[i] = 0; }
+  if (lane == 0) { for (int i = 0; i < 3; i++) QSET(c.w, 9 + i, pos[i]); for (int i = 9; i < 15; i++) c.w->qvel[i] = 0; }
   SYNCW();
   eng_forward(c, lane);
 }
@@ -806,7 +806,7 @@ DEV void task_reset_model(const TaskCtx& c, const float* rv, int lane) {
       if (lane == 0) {
         for (int i = 0; i < 3; i++) { c.s->obj_init[i] = rv[i]; c.w->shift[i] = rv[i] - c.tc->movable_pos0[i]; }
         c.s->target[0] = rv[0] - 0.3f; c.s->target[1] = rv[1] - 0.45f; c.s->target[2] = rv[2];
-        c.w->qpos[9] = 0; c.w->qvel[9] = 0;
+        QSET(c.w, 9, 0); c.w->qvel[9] = 0;
       }
       SYNCW();
       eng_forward(c, lane);
@@ -822,7 +822,7 @@ DEV void task_reset_model(const TaskCtx& c, const float* rv, int lane) {
       if (lane == 0) {
         for (int i = 0; i < 3; i++) c.w->shift[i] = rv[i] - c.tc->movable_pos0[i];
         c.s->target[0] = rv[0]; c.s->target[1] = rv[1] - 0.16f; c.s->target[2] = rv[2] + 0.09f;
-        c.w->qpos[9] = (real)-0.15;
+        QSET(c.w, 9, (real)-0.15);
       }
       SYNCW();
       eng_forward(c, lane);
@@ -834,7 +834,7 @@ DEV void task_reset_model(const TaskCtx& c, const float* rv, int lane) {
       const bool side = c.tc->task_id == T_BUTTON_PRESS || c.tc->task_id == T_BUTTON_PRESS_WALL;
       if (lane == 0) {
         for (int i = 0; i < 3; i++) { c.s->obj_init[i] = rv[i]; c.w->shift[i] = rv[i] - c.tc->movable_pos0[i]; }
-        if (side) { c.w->qpos[9] = 0; c.w->qvel[9] = 0; }
+        if (side) { QSET(c.w, 9, 0); c.w->qvel[9] = 0; }
       }
       SYNCW();
       eng_forward(c, lane);
@@ -854,7 +854,7 @@ DEV void task_reset_model(const TaskCtx& c, const float* rv, int lane) {
       if (id == T_COFFEE_BUTTON) { mug[1] -= (real)0.22; for (int i = 0; i < 3; i++) mach[i] = rv[i]; }
       else { for (int i = 0; i < 3; i++) mach[i] = (id == T_COFFEE_PULL ? rv[i] : rv[3 + i]); mach[1] += (real)0.22; }
       if (lane == 0 && id == T_COFFEE_BUTTON) for (int i = 0; i < 3; i++) c.w->shift[i] = mach[i] - c.tc->movable_pos0[i];   // body pos set BEFORE the forward
-      if (lane == 0) { for (int i = 0; i < 3; i++) c.w->qpos[i] = mug[i]; for (int i = 9; i < 15; i++) c.w->qvel[i] = 0; }
+      if (lane == 0) { for (int i = 0; i < 3; i++) QSET(c.w, i, mug[i]); for (int i = 9; i < 15; i++) c.w->qvel[i] = 0; }
       SYNCW();
       eng_forward(c, lane);
       if (lane == 0) {
@@ -946,7 +946,7 @@ DEV void task_reset_model(const TaskCtx& c, const float* rv, int lane) {
       if (lane == 0) {
         for (int i = 0; i < 3; i++) { c.s->obj_init[i] = rv[i]; c.w->shift[i] = rv[i] - c.tc->movable_pos0[i]; }
         c.s->target[0] = rv[0] + 0.2f; c.s->target[1] = rv[1] - 0.2f; c.s->target[2] = rv[2];
-        c.w->qpos[9] = (real)-1.5708; c.w->qvel[9] = 0;
+        QSET(c.w, 9, (real)-1.5708); c.w->qvel[9] = 0;
       }
       SYNCW();
       eng_forward(c, lane);
@@ -955,7 +955,7 @@ DEV void task_reset_model(const TaskCtx& c, const float* rv, int lane) {
       const bool lock = c.tc->task_id == T_DOOR_LOCK;
       if (lane == 0) {
         for (int i = 0; i < 3; i++) c.w->shift[i] = rv[i] - c.tc->movable_pos0[i];
-        if (!lock) { c.w->qpos[9] = (real)1.5708; c.w->qvel[9] = 0; }
+        if (!lock) { QSET(c.w, 9, (real)1.5708); c.w->qvel[9] = 0; }
       }
       SYNCW();
       if (lock) eng_sim(c, 5, lane); else eng_forward(c, lane);
@@ -987,7 +987,7 @@ DEV void task_reset_model(const TaskCtx& c, const float* rv, int lane) {
         if (!closing) c.s->target[0] = rv[0] + 0.2f;
         real h[3]; mw_frame_pos(c.m, c.w, F_TASK0, h);          // stale kinematics, as in the reference
         c.s->scal[0] = (float)(h[0] + (closing ? (real)0.2 : (real)0)); c.s->scal[1] = (float)h[1]; c.s->scal[2] = (float)h[2];
-        c.w->qpos[9] = closing ? (real)0.2 : (real)0;            // data.joint("window_slide").qpos = ..., no mj_forward
+        QSET(c.w, 9, closing ? (real)0.2 : (real)0);            // data.joint("window_slide").qpos = ..., no mj_forward
       }
       SYNCW();
     } break;
@@ -997,7 +997,7 @@ DEV void task_reset_model(const TaskCtx& c, const float* rv, int lane) {
       const bool pull = id == T_HANDLE_PULL || id == T_HANDLE_PULL_SIDE;
       if (lane == 0) {
         for (int i = 0; i < 3; i++) { c.s->obj_init[i] = rv[i]; c.w->shift[i] = rv[i] - c.tc->movable_pos0[i]; }
-        c.w->qpos[9] = pull ? (real)-0.1 : (real)-0.001; c.w->qvel[9] = 0;
+        QSET(c.w, 9, pull ? (real)-0.1 : (real)-0.001); c.w->qvel[9] = 0;
       }
       SYNCW();
       eng_forward(c, lane);
@@ -1019,8 +1019,8 @@ DEV void task_reset_model(const TaskCtx& c, const float* rv, int lane) {
     case T_PEG_UNPLUG_SIDE: {   // sawyer_peg_unplug_side_v3.py:96-116
       if (lane == 0) {
         for (int i = 0; i < 3; i++) c.w->shift[i] = rv[i] - c.tc->movable_pos0[i];
-        c.w->qpos[9] = rv[0] + (real)0.044; c.w->qpos[10] = rv[1]; c.w->qpos[11] = rv[2] + (real)0.131;
-        c.w->qpos[12] = 1; c.w->qpos[13] = 0; c.w->qpos[14] = 0; c.w->qpos[15] = 0;
+        QSET(c.w, 9, rv[0] + (real)0.044); QSET(c.w, 10, rv[1]); QSET(c.w, 11, rv[2] + (real)0.131);
+        QSET(c.w, 12, 1); QSET(c.w, 13, 0); QSET(c.w, 14, 0); QSET(c.w, 15, 0);
         for (int i = 9; i < 12; i++) c.w->qvel[i] = 0;
       }
       SYNCW();
@@ -1039,8 +1039,8 @@ DEV void task_reset_model(const TaskCtx& c, const float* rv, int lane) {
         for (int i = 0; i < 3; i++) { c.s->obj_init[i] = rv[i]; c.s->target[i] = rv[3 + i]; }
         if (id == T_PLATE_SLIDE) for (int i = 0; i < 3; i++) c.w->shift[i] = rv[3 + i] - c.tc->movable_pos0[i];
         if (id == T_PLATE_SLIDE_BACK_SIDE) for (int i = 0; i < 3; i++) c.w->shift[i] = rv[i] - c.tc->movable_pos0[i];
-        c.w->qpos[9] = id == T_PLATE_SLIDE_BACK_SIDE ? (real)-0.15 : (real)0;
-        c.w->qpos[10] = id == T_PLATE_SLIDE_BACK ? (real)0.15 : (real)0;
+        QSET(c.w, 9, id == T_PLATE_SLIDE_BACK_SIDE ? (real)-0.15 : (real)0);
+        QSET(c.w, 10, id == T_PLATE_SLIDE_BACK ? (real)0.15 : (real)0);
       }
       SYNCW();
       eng_forward(c, lane);
@@ -1072,7 +1072,7 @@ DEV void task_reset_model(const TaskCtx& c, const float* rv, int lane) {
       }
       SYNCW();
       set_obj_xyz(c, p, lane);                                         // _set_stick_xyz: qpos[9:12], qvel[9:15] = 0, forward
-      if (lane == 0) { c.w->qpos[16] = 0; c.w->qpos[17] = pull ? (real)0.09 : (real)0; c.w->qvel[16] = 0; }   // qvel[16:18] on nv = 17 reaches dof 16 only
+      if (lane == 0) { QSET(c.w, 16, 0); QSET(c.w, 17, pull ? (real)0.09 : (real)0); c.w->qvel[16] = 0; }   // qvel[16:18] on nv = 17 reaches dof 16 only
       SYNCW();
       eng_forward(c, lane);
       if (lane == 0) { real o[3]; mw_frame_pos(c.m, c.w, F_TASK0 + 2, o); for (int i = 0; i < 3; i++) c.s->obj_init[i] = (float)o[i]; }

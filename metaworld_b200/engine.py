@@ -23,11 +23,11 @@ SO64_PATH = os.path.join(_HERE, "libmwb200_f64.so")   # same kernels with real=d
 TASKCONST_DTYPE = np.dtype([("task_id", "i4"), ("nframe_task", "i4"), ("main_geom", "i4"), ("pad", "i4"),
                             ("hand_init", "f4", 3), ("mocap_lo", "f4", 3), ("mocap_hi", "f4", 3),
                             ("goal_lo", "f4", 3), ("goal_hi", "f4", 3), ("movable_pos0", "f4", 3), ("p", "f4", 16)])
-ENVSTATE_DTYPE = np.dtype([("qpos", "f4", 18), ("qvel", "f4", 17), ("warm", "f4", 17), ("mocap_pos", "f4", 3),
+ENVSTATE_DTYPE = np.dtype([("qpos", "f8", 18), ("qvel", "f4", 17), ("warm", "f4", 17), ("mocap_pos", "f4", 3),
                            ("prev_obs", "f4", 18), ("shift", "f4", 3), ("target", "f4", 3), ("obj_init", "f4", 3),
                            ("init_tcp", "f4", 3), ("scal", "f4", 16), ("path_len", "f4"),
                            ("partially_observable", "f4"), ("snapshot", "f4"), ("episode", "f4"), ("ep_return", "f4"),
-                           ("pad", "f4", 22)])
+                           ("pad", "f4", 4)])
 SNAPSHOT_DTYPE = np.dtype([("st", ENVSTATE_DTYPE), ("obs", "f4", 39), ("pad", "f4", 25)])
 INFO_KEYS = ["success", "near_object", "grasp_success", "grasp_reward", "in_place_reward", "obj_to_target",
              "unscaled_reward"]

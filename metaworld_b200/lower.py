@@ -33,6 +33,7 @@ NPARAM = 12
 
 # (name, ctype, shape)
 FIELDS = [
+    ("qpos0d", "f8", (MAXNQ,)),     # float64 copy of qpos0 (mj_resetData must reproduce free-joint initial poses exactly)
     ("nlink", "i4", ()), ("nq", "i4", ()), ("nv", "i4", ()), ("ngeom", "i4", ()), ("npair", "i4", ()),
     ("nframe", "i4", ()), ("nmeshvert", "i4", ()), ("pad0", "i4", ()),
     ("timestep", "f4", ()), ("solver_scale", "f4", ()), ("gravity", "f4", (3,)), ("tolerance", "f4", ()),
@@ -78,7 +79,7 @@ F_HAND, F_RCLAW, F_LCLAW, F_RPAD, F_LPAD, F_REE, F_LEE, F_TASK0 = range(8)
 
 
 def emit_header() -> str:
-    ctype = {"i4": "int", "u4": "unsigned int", "f4": "float", "u1": "unsigned char"}
+    ctype = {"i4": "int", "u4": "unsigned int", "f4": "float", "u1": "unsigned char", "f8": "double"}
     lines = ["/* GENERATED by metaworld_b200/lower.py:emit_header -- do not edit. */", "#pragma once",
              f"#define MW_MAXLINK {MAXLINK}", f"#define MW_MAXDOF {MAXDOF}", f"#define MW_MAXNQ {MAXNQ}",
              f"#define MW_MAXGEOM {MAXGEOM}", f"#define MW_MAXPAIR {MAXPAIR}", f"#define MW_MAXPARAM {MAXPARAM}",
@@ -225,6 +226,7 @@ def lower(m: mjcf.Model, movable: str | None, task_frames=()) -> Lowered:
         r["dof_springref"][d] = a["qpos_spring"][a["jnt_qposadr"][j]] if a["jnt_type"][j] != JNT_FREE else 0.0
         assert a["jnt_margin"][j] == 0
     r["qpos0"][: m.nq] = a["qpos0"]
+    r["qpos0d"][: m.nq] = a["qpos0"]
     r["nlink"], r["nq"], r["nv"] = nl, m.nq, nv
     r["timestep"] = m.opt["timestep"]
     r["solver_scale"] = 1.0 / (m.opt["meaninertia"] * max(1, nv))
