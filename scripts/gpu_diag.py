@@ -103,6 +103,7 @@ def do_open(task):
 def do_cr(task):
     g = np.load(os.path.join(GOLD, f"traj_{task}.npz"))
     rig = Rig(torch, task, g["p_rand_vec"]); rig.reset()
+    rig.step(g["p_actions"][:, 0])     # like the test: rewards that latch state on their first call latch here
     nq, nv = g["p_qpos"].shape[2], g["p_qvel"].shape[2]
     worst = (-1, 0, 0)
     for t in range(g["p_actions"].shape[1] - 1):
