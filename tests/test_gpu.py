@@ -29,7 +29,8 @@ _JAMMED = "resting contacts under load are chaotic: float32 step vs float64 orac
 _TOUCH = "object starts exactly touching (dist == margin to the last bit): contact inclusion differs between float32 and float64 state"
 SENSITIVE_RESET = {"disassemble-v3": _JAMMED, "peg-unplug-side-v3": _JAMMED}
 SENSITIVE_OPEN_LOOP = {"assembly-v3": _JAMMED, "basketball-v3": _TOUCH, "box-close-v3": _JAMMED, "coffee-push-v3": _JAMMED,
-                       "disassemble-v3": _JAMMED, "handle-press-v3": _JAMMED}
+                       "disassemble-v3": _JAMMED,
+                       "handle-press-v3": "observations agree to 3e-6; the reward (slope ~50 near the handle) turns that into 1.4e-4"}
 SENSITIVE_ONE_STEP = {"assembly-v3": "the nut rests on the peg (mesh-cylinder contacts under load): single steps reach 1.2e-4"}
 SENSITIVE_CONTACT_RICH = {"soccer-v3": "mesh-mesh face contact (hand against the goal frame): EPA witness point on a flat patch is path dependent"}
 
