@@ -131,10 +131,12 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
         self.d_actions = torch.zeros(N, 4, device=dev)
         self.d_next = torch.zeros(N, dtype=torch.int32, device=dev)
         self.d_cur = torch.zeros(N, dtype=torch.int32, device=dev)
-        self.h_actions = torch.zeros(N, 4).pin_memory()
-        self.h_next = torch.zeros(N, dtype=torch.int32).pin_memory()
-        self.h_obs = torch.zeros(N, self.obs_dim).pin_memory()
-        self.h_small = torch.zeros(N, 9).pin_memory()      # reward, info[7], flags
+        on_gpu = self.device.type == "cuda"      # (the host-logic tests drive this class with a CPU stand-in for the engine)
+        pin = (lambda t: t.pin_memory()) if on_gpu else (lambda t: t)
+        self.h_actions = pin(torch.zeros(N, 4))
+        self.h_next = pin(torch.zeros(N, dtype=torch.int32))
+        self.h_obs = pin(torch.zeros(N, self.obs_dim))
+        self.h_small = pin(torch.zeros(N, 9))      # reward, info[7], flags
         self._ep_len = np.zeros(N, dtype=np.int64)
         self._closed = False
         self._needs_reset = True
@@ -197,7 +199,8 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
         small = t.cat([self.d_reward[:, None], self.d_info, (self.d_term + 2 * self.d_trunc).float()[:, None]], dim=1)
         self.h_small.copy_(small, non_blocking=True)
         self.h_obs.copy_(self.d_obs, non_blocking=True)
-        t.cuda.current_stream(self.device).synchronize()
+        if self.device.type == "cuda":
+            t.cuda.current_stream(self.device).synchronize()
         sm = self.h_small.numpy()
         obs = self.h_obs.numpy().astype(self.obs_dtype)
         reward = sm[:, 0].astype(np.float64)
