@@ -110,13 +110,16 @@ def test_cabi_exports_every_declared_symbol(built):
     hdr = open(os.path.join(ROOT, "include", "metaworld_b200.h")).read()
     names = set(re.findall(r"\b(mw_[a-z_0-9]+)\s*\(", hdr))
     assert {"mw_create", "mw_step", "mw_reset", "mw_build_snapshots", "mw_destroy"} <= names
-    lib = ctypes.CDLL(os.path.join(ROOT, "metaworld_b200", "libmwb200.so"))
-    for n in names:
-        assert hasattr(lib, n), f"{n} declared in include/metaworld_b200.h but not exported"
-    lib.mw_sizeof_envstate.restype = ctypes.c_int
-    assert lib.mw_sizeof_envstate() == 512 and lib.mw_sizeof_snapshot() == 768
     from metaworld_b200 import lower
-    assert lib.mw_sizeof_model() == lower.DTYPE.itemsize
+    for so in ("libmwb200.so", "libmwb200_f64.so"):      # the float32 step engine and the float64 snapshot builder: same ABI, same records
+        lib = ctypes.CDLL(os.path.join(ROOT, "metaworld_b200", so))
+        for n in names:
+            assert hasattr(lib, n), f"{n} declared in include/metaworld_b200.h but not exported by {so}"
+        lib.mw_sizeof_envstate.restype = ctypes.c_int
+        assert lib.mw_sizeof_envstate() == 512 and lib.mw_sizeof_snapshot() == 768
+        assert lib.mw_sizeof_model() == lower.DTYPE.itemsize
+        lib.mw_build_info.restype = ctypes.c_char_p
+        assert (b"real=double" if "f64" in so else b"real=float") in lib.mw_build_info()
     # no CPU fallback: creating an engine without a CUDA device must fail loudly
     from metaworld_b200 import engine
     import torch
