@@ -62,13 +62,14 @@ int mw_reset(mw_engine*, int n, const int* env_ids /*DEV or NULL*/, const int* s
  * SawyerXYZEnv.step, metaworld/sawyer_xyz_env.py:580-642 + TimeLimit + AutoTerminateOnSuccessWrapper,
  * metaworld/wrappers.py:207-230).  All arrays DEV, n_envs rows:
  *   actions [n,4] f32; obs [n,obs_stride] f32 (39 written); reward [n] f32; terminated/truncated [n] u8;
- *   info [n,7] f32 = success, near_object, grasp_success, grasp_reward, in_place_reward, obj_to_target,
- *   unscaled_reward; final_obs [n,obs_stride] / final_info [n,8] (7 infos + episode return) are written
+ *   info [n,info_stride] f32, columns 0..6 = success, near_object, grasp_success, grasp_reward, in_place_reward,
+ *   obj_to_target, unscaled_reward; when info_stride >= 9 also column 7 = reward and column 8 = terminated + 2*truncated
+ *   (one packed record per env for a single device->host copy); final_obs [n,obs_stride] / final_info [n,8] (7 infos + episode return) are written
  *   only for rows whose episode ended in this call (terminated|truncated), which then restart from
  *   next_snapshot[i] (or, when next_snapshot is NULL, from a snapshot drawn on the device from the env's
  *   own goal set, see mw_set_goal_sets).                                                             */
 int mw_step(mw_engine*, const float* actions, float* obs, int obs_stride, float* reward,
-            unsigned char* terminated, unsigned char* truncated, float* info, float* final_obs,
+            unsigned char* terminated, unsigned char* truncated, float* info, int info_stride, float* final_obs,
             float* final_info, const int* next_snapshot, void* stream);
 
 /* options: max_episode_steps (TimeLimit), terminate_on_success (0/1), device sampler seed */
@@ -96,11 +97,19 @@ int mw_get_counters(mw_engine*, unsigned long long* out5);
  * call it after a few warm-up steps and then rarely.                                                                */
 int mw_rebalance(mw_engine*);
 
+/* Profiling switch (default off: the timed kernel then carries no profiling atomics).  When on, mw_step additionally sums
+ * the per-phase counters below, the per-model cost used by mw_rebalance, and records per env [20] u32: the 13 counters of
+ * mw_get_profile for that env's last step, [13] solver iterations, [14] / [15] largest contact / constraint-row
+ * count over the 6 passes, [16] launch slot (CTA).  Stands in for nothing in the reference (it has no profiler hook on this path).  */
+int mw_set_profiling(mw_engine*, int on);
+int mw_get_env_profile(mw_engine*, unsigned* out /*host [n_envs*20]*/);
+
 /* per-phase SM cycle counters summed over all env steps since the last call (one warp = one env, so these are
  * warp-cycles): [0] kinematics + mass matrix, [1] collision (incl. [2]), [2] GJK/EPA pairs, [3] constraint rows,
  * [4] bias forces + unconstrained solve, [5] constraint solver, [6] integration + glue, [7] obs / reward / autoreset,
- * [8] whole step; events: [9] GJK/EPA pair calls, [10] EPA expansions, [11] GJK iterations */
-int mw_get_profile(mw_engine*, unsigned long long* out12);
+ * [8] whole step incl. [12]; events: [9] GJK/EPA pair calls, [10] EPA expansions, [11] GJK iterations; [12] cycles spent
+ * waiting for the CTA's other warps at phase boundaries (not part of [0]..[7]) */
+int mw_get_profile(mw_engine*, unsigned long long* out13);
 /* warp cycles each environment spent in its most recent step (host array of n_envs) */
 int mw_get_env_cost(mw_engine*, unsigned* out);
 

@@ -22,6 +22,7 @@
 #define WARPS_PER_BLOCK 7
 #endif
 #define BLOCK_THREADS (WARPS_PER_BLOCK * 32)
+#define MW_ENVPROF_W 20       // words per env in the optional per-env profile record (mw_get_env_profile)
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -35,9 +36,10 @@ struct EngineDev {
   const int* goal_first; const int* goal_count;      // device sampler ranges (may be NULL)
   int* diag;                                         // [n_envs][2]: contacts dropped, solver iterations
   EpaWs* epa;                                        // GJK/EPA polytope workspace, one per launched warp (global memory)
-  unsigned long long* prof;                          // [12] summed cycle / event counters (mw_get_profile)
+  unsigned long long* prof;                          // [16] summed cycle / event counters (mw_get_profile)
   unsigned long long* model_cycles;                  // [n_models][2]: warp cycles, env steps (drives mw_rebalance)
   unsigned* env_cost;                                // [n_envs] warp cycles of each env's previous step (drives the launch order)
+  unsigned* env_prof;                                // optional [n_envs][16] per-env phase cycles / event counts of the last step (mw_set_profiling)
   int n_envs, max_steps, terminate_on_success; unsigned long long seed;
 };
 
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1)
 k_step(EngineDev e, const int* __restrict__ block_order, const int* __restrict__ block_model, const int* __restrict__ block_start, const int* __restrict__ block_count,
        const int* __restrict__ perm, const float* __restrict__ actions, float* __restrict__ obs_out, int obs_stride,
        float* __restrict__ reward, unsigned char* __restrict__ terminated, unsigned char* __restrict__ truncated,
-       float* __restrict__ info_out, float* __restrict__ final_obs, float* __restrict__ final_info, const int* __restrict__ next_snapshot) {
+       float* __restrict__ info_out, int info_stride, float* __restrict__ final_obs, float* __restrict__ final_info, const int* __restrict__ next_snapshot) {
   extern __shared__ __align__(16) unsigned char smem[];
   BlockShared* bs = (BlockShared*)smem;
   WarpShared* wsa = (WarpShared*)(smem + sizeof(BlockShared));
@@ -146,7 +148,7 @@ k_step(EngineDev e, const int* __restrict__ block_order, const int* __restrict__
   WarpScratch* w = &ws->w;
   const MwModel* m = (const MwModel*)bs->model;
   load_env(ws, e.state + env, lane);
-  if (lane < 12) w->prof[lane] = 0;
+  if (lane < 16) w->prof[lane] = 0;
   const long long t_begin = clock64();
   real act[4];
   for (int i = 0; i < 4; i++) act[i] = fmin(fmax((real)actions[4 * env + i], (real)-1), (real)1);
@@ -155,10 +157,14 @@ k_step(EngineDev e, const int* __restrict__ block_order, const int* __restrict__
   if (lane < 3) w->mocap_pos[lane] = fmin(fmax(w->mocap_pos[lane] + act[lane] * (real)0.01, (real)bs->tc.mocap_lo[lane]), (real)bs->tc.mocap_hi[lane]);
   if (lane == 0) { w->ctrl[0] = (real)actions[4 * env + 3]; w->ctrl[1] = -(real)actions[4 * env + 3]; }
   SYNCW();
-  int iters = 0, dropped = 0;
-  for (int s = 0; s < 5; s++) { mw_forward(m, c.meshvert, w, lane); iters += w->solver_iter; dropped += w->ncon_dropped; mw_euler(m, w, lane); }
+  int iters = 0, dropped = 0, ncon_max = 0, nefc_max = 0;
+  for (int s = 0; s < 5; s++) {
+    mw_forward(m, c.meshvert, w, lane);
+    iters += w->solver_iter; dropped += w->ncon_dropped; ncon_max = max(ncon_max, w->ncon); nefc_max = max(nefc_max, w->nefc);
+    mw_euler(m, w, lane);
+  }
   mw_forward(m, c.meshvert, w, lane);
-  iters += w->solver_iter; dropped += w->ncon_dropped;
+  iters += w->solver_iter; dropped += w->ncon_dropped; ncon_max = max(ncon_max, w->ncon); nefc_max = max(nefc_max, w->nefc);
   bool done = false;
   const long long t_phys = clock64();
   if (lane == 0) {
@@ -175,17 +181,30 @@ k_step(EngineDev e, const int* __restrict__ block_order, const int* __restrict__
     bool trunc = ws->es.path_len >= (float)e.max_steps;
     bool term = e.terminate_on_success && inf[INFO_SUCCESS] == (real)1;
     reward[env] = (float)rew; terminated[env] = term; truncated[env] = trunc;
+    if (info_stride >= 9) { info_out[(size_t)env * info_stride + 7] = (float)rew; info_out[(size_t)env * info_stride + 8] = (float)((int)term + 2 * (int)trunc); }   // packed record: one D2H copy
     ws->info[7] = (term || trunc) ? 1.f : 0.f;
     e.diag[2 * env] += dropped; e.diag[2 * env + 1] += iters;
     w->prof[7] = clock64() - t_phys; w->prof[8] = clock64() - t_begin;
-    e.env_cost[env] = (unsigned)(w->prof[8] > 0xFFFFFFFFll ? 0xFFFFFFFFll : w->prof[8]);
-    w->prof[6] = w->prof[8] - w->prof[7] - (w->prof[0] + w->prof[1] + w->prof[3] + w->prof[4] + w->prof[5]);   // euler + glue
+    // launch-order key: this env's OWN work.  (The whole-step time is the same for all warps of a CTA -- they wait for
+    // each other at every phase boundary -- and would keep light envs glued to the heavy one they were once grouped with.)
+    const long long own = w->prof[8] - w->prof[12];
+    e.env_cost[env] = (unsigned)(own > 0xFFFFFFFFll ? 0xFFFFFFFFll : own);
+    w->prof[6] = own - w->prof[7] - (w->prof[0] + w->prof[1] + w->prof[3] + w->prof[4] + w->prof[5]);   // euler + glue
   }
   SYNCW();
-  if (lane < 12 && e.prof) atomicAdd(e.prof + lane, (unsigned long long)w->prof[lane]);
-  if (lane == 0 && e.model_cycles) { atomicAdd(e.model_cycles + 2 * mi, (unsigned long long)w->prof[8]); atomicAdd(e.model_cycles + 2 * mi + 1, 1ull); }
+  if (e.prof) {     // profiling runs only (mw_set_profiling): summed phase counters, per-model cost, per-env record
+    if (lane < 13) atomicAdd(e.prof + lane, (unsigned long long)w->prof[lane]);
+    if (lane == 0 && e.model_cycles) { atomicAdd(e.model_cycles + 2 * mi, (unsigned long long)w->prof[8]); atomicAdd(e.model_cycles + 2 * mi + 1, 1ull); }
+    if (e.env_prof) {
+      if (lane < 13) e.env_prof[MW_ENVPROF_W * env + lane] = (unsigned)(w->prof[lane] > 0xFFFFFFFFll ? 0xFFFFFFFFll : w->prof[lane]);
+      if (lane == 13) e.env_prof[MW_ENVPROF_W * env + 13] = (unsigned)iters;
+      if (lane == 14) e.env_prof[MW_ENVPROF_W * env + 14] = (unsigned)ncon_max;
+      if (lane == 15) e.env_prof[MW_ENVPROF_W * env + 15] = (unsigned)nefc_max;
+      if (lane == 16) e.env_prof[MW_ENVPROF_W * env + 16] = (unsigned)blockIdx.x;
+    }
+  }
   done = ws->info[7] != 0.f;
-  if (lane < INFO_N) info_out[(size_t)env * INFO_N + lane] = ws->info[lane];
+  if (lane < INFO_N) info_out[(size_t)env * info_stride + lane] = ws->info[lane];
   if (!done) {
     for (int i = lane; i < 39; i += 32) obs_out[(size_t)env * obs_stride + i] = ws->obs[i];
     store_env(ws, e.state + env, lane);
@@ -235,7 +254,7 @@ k_snapshot(EngineDev e, const int* __restrict__ block_model, const int* __restri
   if (lane < 3) w->shift[lane] = 0;
   SYNCW();
   for (int pass = 0; pass < 2; pass++) {
-    if (pass == 1 || true) {
+    {
       // mj_resetData (pass 0: a freshly constructed env is in the same state)
       if (lane < MW_MAXNQ) QSET(w, lane, lane < m->nq ? m->qpos0d[lane] : 0.0);
       if (lane < MW_MAXDOF) { w->qvel[lane] = 0; w->warm[lane] = 0; }
@@ -372,7 +391,7 @@ struct mw_engine {
   MwEnvState* d_state = nullptr; MwSnapshot* d_snaps = nullptr; int snap_cap = 0, n_snaps = 0;
   int *d_goal_first = nullptr, *d_goal_count = nullptr, *d_diag = nullptr;
   EpaWs* d_epa = nullptr; size_t epa_cap = 0;
-  unsigned long long* d_prof = nullptr; unsigned long long* d_model_cycles = nullptr;
+  unsigned long long* d_prof = nullptr; unsigned long long* d_model_cycles = nullptr; unsigned* d_env_prof = nullptr; int profiling = 0;
   unsigned* d_env_cost = nullptr; int *d_block_order = nullptr, *d_model_first = nullptr, *d_model_count = nullptr; int n_sorted_models = 0;
   std::vector<int> env_model; std::vector<int> model_order;   // block table inputs (mw_rebalance re-sorts the models by measured cost)
   // env block table
@@ -381,7 +400,7 @@ struct mw_engine {
   unsigned long long launches = 0, env_steps = 0;
   EngineDev dev() const {
     EngineDev e; e.models = d_models; e.model_stride = model_stride; e.taskconsts = d_tc; e.meshverts = d_meshptrs;
-    e.state = d_state; e.snaps = d_snaps; e.goal_first = d_goal_first; e.goal_count = d_goal_count; e.diag = d_diag; e.epa = d_epa; e.prof = d_prof; e.model_cycles = d_model_cycles; e.env_cost = d_env_cost;
+    e.state = d_state; e.snaps = d_snaps; e.goal_first = d_goal_first; e.goal_count = d_goal_count; e.diag = d_diag; e.epa = d_epa; e.prof = profiling ? d_prof : nullptr; e.model_cycles = d_model_cycles; e.env_cost = d_env_cost; e.env_prof = profiling ? d_env_prof : nullptr;
     e.n_envs = n_envs; e.max_steps = max_steps; e.terminate_on_success = terminate_on_success; e.seed = seed; return e;
   }
 };
@@ -480,8 +499,8 @@ int mw_create(mw_engine** out, int device, int n_models, const void* models, con
   CK(cudaMemcpy(E->d_meshptrs, ptrs.data(), sizeof(float*) * n_models, cudaMemcpyHostToDevice));
   CK(cudaMalloc((void**)&E->d_model_cycles, sizeof(unsigned long long) * 2 * n_models));
   CK(cudaMemset(E->d_model_cycles, 0, sizeof(unsigned long long) * 2 * n_models));
-  CK(cudaMalloc((void**)&E->d_prof, sizeof(unsigned long long) * 12));
-  CK(cudaMemset(E->d_prof, 0, sizeof(unsigned long long) * 12));
+  CK(cudaMalloc((void**)&E->d_prof, sizeof(unsigned long long) * 16));
+  CK(cudaMemset(E->d_prof, 0, sizeof(unsigned long long) * 16));
   CK(cudaFuncSetAttribute(k_order_envs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned long long) * MW_SORT_MAX)));
   CK(cudaFuncSetAttribute(k_order_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned long long) * MW_SORT_MAX)));
   CK(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
@@ -496,7 +515,7 @@ void mw_destroy(mw_engine* E) {
   cudaSetDevice(E->device);
   cudaFree(E->d_models); cudaFree(E->d_tc); cudaFree(E->d_meshptrs);
   for (float* p : E->meshbufs) cudaFree(p);
-  cudaFree(E->d_state); cudaFree(E->d_snaps); cudaFree(E->d_goal_first); cudaFree(E->d_goal_count); cudaFree(E->d_diag); cudaFree(E->d_epa); cudaFree(E->d_prof); cudaFree(E->d_model_cycles); cudaFree(E->d_env_cost); cudaFree(E->d_block_order); cudaFree(E->d_model_first); cudaFree(E->d_model_count);
+  cudaFree(E->d_state); cudaFree(E->d_snaps); cudaFree(E->d_goal_first); cudaFree(E->d_goal_count); cudaFree(E->d_diag); cudaFree(E->d_epa); cudaFree(E->d_prof); cudaFree(E->d_model_cycles); cudaFree(E->d_env_prof); cudaFree(E->d_env_cost); cudaFree(E->d_block_order); cudaFree(E->d_model_first); cudaFree(E->d_model_count);
   cudaFree(E->d_block_model); cudaFree(E->d_block_start); cudaFree(E->d_block_count); cudaFree(E->d_perm);
   delete E;
 }
@@ -515,6 +534,8 @@ int mw_set_envs(mw_engine* E, int n_envs, const int* env_model) {
   if (E->d_state) cudaFree(E->d_state);
   CK(cudaMalloc((void**)&E->d_state, sizeof(MwEnvState) * n_envs));
   CK(cudaMemset(E->d_state, 0, sizeof(MwEnvState) * n_envs));
+  if (E->d_env_prof) { cudaFree(E->d_env_prof); E->d_env_prof = nullptr; }
+  if (E->profiling) { CK(cudaMalloc((void**)&E->d_env_prof, sizeof(unsigned) * MW_ENVPROF_W * n_envs)); CK(cudaMemset(E->d_env_prof, 0, sizeof(unsigned) * MW_ENVPROF_W * n_envs)); }
   if (E->d_diag) cudaFree(E->d_diag);
   CK(cudaMalloc((void**)&E->d_diag, sizeof(int) * 2 * n_envs));
   CK(cudaMemset(E->d_diag, 0, sizeof(int) * 2 * n_envs));
@@ -582,9 +603,9 @@ int mw_reset(mw_engine* E, int n, const int* env_ids, const int* snapshot_ids, f
 }
 
 int mw_step(mw_engine* E, const float* actions, float* obs, int obs_stride, float* reward, unsigned char* terminated, unsigned char* truncated,
-            float* info, float* final_obs, float* final_info, const int* next_snapshot, void* stream) {
+            float* info, int info_stride, float* final_obs, float* final_info, const int* next_snapshot, void* stream) {
   if (!E || !E->d_state) return fail(MW_ERR_STATE, "mw_step: mw_set_envs not called");
-  if (!actions || !obs || !reward || !terminated || !truncated || !info || obs_stride < 39) return fail(MW_ERR_ARG, "mw_step: bad arguments");
+  if (!actions || !obs || !reward || !terminated || !truncated || !info || obs_stride < 39 || info_stride < 7) return fail(MW_ERR_ARG, "mw_step: bad arguments");
   if (!next_snapshot && !E->d_goal_first) return fail(MW_ERR_STATE, "mw_step: no next_snapshot and no goal sets for the device sampler");
   CK(cudaSetDevice(E->device));
   {   // launch order from the previous step's per-env cost (see k_order_*)
@@ -594,7 +615,7 @@ int mw_step(mw_engine* E, const float* actions, float* obs, int obs_stride, floa
     k_order_blocks<<<1, 1024, sizeof(unsigned long long) * Pb, (cudaStream_t)stream>>>(E->n_blocks, E->d_block_start, E->d_perm, E->d_env_cost, E->d_block_order);
   }
   k_step<<<E->n_blocks, BLOCK_THREADS, smem_bytes(), (cudaStream_t)stream>>>(E->dev(), E->d_block_order, E->d_block_model, E->d_block_start, E->d_block_count, E->d_perm,
-      actions, obs, obs_stride, reward, terminated, truncated, info, final_obs, final_info, next_snapshot);
+      actions, obs, obs_stride, reward, terminated, truncated, info, info_stride, final_obs, final_info, next_snapshot);
   CK(cudaGetLastError());
   E->launches += 3; E->env_steps += (unsigned long long)E->n_envs;
   return MW_OK;
@@ -669,6 +690,20 @@ int mw_rebalance(mw_engine* E) {
   return MW_OK;
 }
 
+int mw_set_profiling(mw_engine* E, int on) {
+  if (!E) return fail(MW_ERR_ARG, "mw_set_profiling");
+  CK(cudaSetDevice(E->device));
+  E->profiling = on ? 1 : 0;
+  if (on && E->n_envs && !E->d_env_prof) { CK(cudaMalloc((void**)&E->d_env_prof, sizeof(unsigned) * MW_ENVPROF_W * E->n_envs)); CK(cudaMemset(E->d_env_prof, 0, sizeof(unsigned) * MW_ENVPROF_W * E->n_envs)); }
+  return MW_OK;
+}
+int mw_get_env_profile(mw_engine* E, unsigned* out) {
+  if (!E || !out || !E->d_env_prof) return fail(MW_ERR_STATE, "mw_get_env_profile: profiling is off (mw_set_profiling)");
+  CK(cudaSetDevice(E->device));
+  CK(cudaMemcpy(out, E->d_env_prof, sizeof(unsigned) * MW_ENVPROF_W * E->n_envs, cudaMemcpyDeviceToHost));
+  return MW_OK;
+}
+
 int mw_get_env_cost(mw_engine* E, unsigned* out) {
   if (!E || !out || !E->d_env_cost) return fail(MW_ERR_ARG, "mw_get_env_cost");
   CK(cudaSetDevice(E->device));
@@ -676,11 +711,11 @@ int mw_get_env_cost(mw_engine* E, unsigned* out) {
   return MW_OK;
 }
 
-int mw_get_profile(mw_engine* E, unsigned long long* out12) {
-  if (!E || !out12) return fail(MW_ERR_ARG, "mw_get_profile");
+int mw_get_profile(mw_engine* E, unsigned long long* out13) {
+  if (!E || !out13) return fail(MW_ERR_ARG, "mw_get_profile");
   CK(cudaSetDevice(E->device));
-  CK(cudaMemcpy(out12, E->d_prof, sizeof(unsigned long long) * 12, cudaMemcpyDeviceToHost));
-  CK(cudaMemset(E->d_prof, 0, sizeof(unsigned long long) * 12));
+  CK(cudaMemcpy(out13, E->d_prof, sizeof(unsigned long long) * 13, cudaMemcpyDeviceToHost));
+  CK(cudaMemset(E->d_prof, 0, sizeof(unsigned long long) * 16));
   return MW_OK;
 }
 

@@ -51,7 +51,7 @@ struct WarpScratch {
   Contact con[MW_MAXCON];
   unsigned short cand[64];
   int ncon, nefc, nscalar, nweld, solver_iter, ncon_dropped;
-  long long prof[12];       // cycle / event counters of this step (see MW_PROF_* in mw_engine.cu; lane 0 only)
+  long long prof[16];       // cycle / event counters of this step (mw_get_profile order; [12] = cycles spent waiting in PHASE_SYNC; lane 0 only)
 };
 
 #define SYNCW() __syncwarp()
@@ -713,9 +713,7 @@ __device__ __noinline__ void mw_solve(const MwModel* __restrict__ m, WarpScratch
     real gauss = warp_sum((real)0.5 * (a - a0) * (Maa - qfs));
     real c = gauss + mw_constraint_eval(w, lane, false);
     SYNCW();
-    if (pass == 0 || c < cost) { cost = c; qacc = a; Ma = Maa; if (pass == 1 || true) {} }
-    if (pass == 0) { /* keep jar of pass 0 only if it wins: recompute below */ }
-    else if (!(c <= cost)) { /* pass 1 lost: recompute jar for the warm start */ }
+    if (pass == 0 || c < cost) { cost = c; qacc = a; Ma = Maa; }
   }
   // recompute jar for the selected start (cheap, avoids branching on which pass won)
   if (lane < nv) w->vTmp[lane] = qacc;
@@ -811,9 +809,11 @@ __device__ __noinline__ void mw_solve(const MwModel* __restrict__ m, WarpScratch
 #define PHASE_SYNC() __syncthreads()
 __device__ __noinline__ void mw_forward(const MwModel* __restrict__ m, const float* __restrict__ meshvert, WarpScratch* w, int lane) {
   const int nv = m->nv;
-  PHASE_SYNC();
   long long t0 = clock64(), t1;
-#define PROF_(i) { t1 = clock64(); if (lane == 0) w->prof[i] += t1 - t0; t0 = t1; PHASE_SYNC(); }
+  PHASE_SYNC();
+  t1 = clock64(); if (lane == 0) w->prof[12] += t1 - t0; t0 = t1;
+  // own work goes to prof[i]; the time spent waiting for the CTA's other warps at the phase boundary goes to prof[12]
+#define PROF_(i) { t1 = clock64(); if (lane == 0) w->prof[i] += t1 - t0; PHASE_SYNC(); t0 = clock64(); if (lane == 0) w->prof[12] += t0 - t1; }
   mw_kinematics(m, w, lane);
   LaneDof L; mw_lane_dof(m, w, lane, &L);
   mw_mass_matrix(m, w, L, lane);

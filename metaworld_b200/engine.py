@@ -53,7 +53,7 @@ def _load(path):
     L.mw_num_snapshots.argtypes = [vp]
     L.mw_get_snapshots.argtypes = [vp, ip, ip, vp]
     L.mw_reset.argtypes = [vp, ip, vp, vp, vp, ip, vp]
-    L.mw_step.argtypes = [vp, vp, vp, ip, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.mw_step.argtypes = [vp, vp, vp, ip, vp, vp, vp, vp, ip, vp, vp, vp, vp]
     L.mw_set_options.argtypes = [vp, ip, ip, C.c_ulonglong]
     L.mw_set_goal_sets.argtypes = [vp, vp, vp]
     L.mw_get_state.argtypes = [vp, vp]
@@ -64,6 +64,8 @@ def _load(path):
     L.mw_get_profile.argtypes = [vp, vp]
     L.mw_rebalance.argtypes = [vp]
     L.mw_get_env_cost.argtypes = [vp, vp]
+    L.mw_set_profiling.argtypes = [vp, ip]
+    L.mw_get_env_profile.argtypes = [vp, vp]
     assert L.mw_sizeof_model() == lower.DTYPE.itemsize, "MwModel layout mismatch (rebuild the library)"
     assert L.mw_sizeof_taskconst() == TASKCONST_DTYPE.itemsize
     assert L.mw_sizeof_envstate() == ENVSTATE_DTYPE.itemsize == 512
@@ -223,7 +225,7 @@ class Engine:
 
     def step(self, actions, obs, reward, terminated, truncated, info, final_obs=None, final_info=None, next_snapshot=None):
         _ck(lib().mw_step(self.h, self._p(actions), self._p(obs), obs.stride(0), self._p(reward), self._p(terminated),
-                          self._p(truncated), self._p(info), self._p(final_obs), self._p(final_info),
+                          self._p(truncated), self._p(info), info.stride(0), self._p(final_obs), self._p(final_info),
                           self._p(next_snapshot), self._stream()))
 
     def get_state(self):
@@ -253,14 +255,26 @@ class Engine:
         return a[:, :ncw].reshape(self.n_envs, -1, 12), a[:, ncw:ncw + 17], a[:, ncw + 17:]
 
     PROFILE_KEYS = ["kin_mass", "collide", "gjk_epa", "constraints", "bias_smooth", "solver", "euler_glue", "obs_reward", "step",
-                    "n_convex_pairs", "n_epa_expansions", "n_gjk_iters"]
+                    "n_convex_pairs", "n_epa_expansions", "n_gjk_iters", "barrier_wait"]
 
     def profile(self):
         """Per-phase warp-cycle counters summed over all env steps since the last call (mw_get_profile)."""
-        out = np.zeros(12, dtype=np.uint64)
+        out = np.zeros(13, dtype=np.uint64)
         self.torch.cuda.synchronize(self.device)
         _ck(lib().mw_get_profile(self.h, out.ctypes.data))
         return dict(zip(self.PROFILE_KEYS, (int(x) for x in out)))
+
+    def set_profiling(self, on=True):
+        """Per-phase cycle counters are collected only while this is on (the timed kernel carries no profiling atomics)."""
+        _ck(lib().mw_set_profiling(self.h, int(bool(on))))
+
+    def env_profile(self):
+        """[n_envs, 20] uint32: PROFILE_KEYS (13) for each env's last step, then [13] solver iterations, [14] ncon max,
+        [15] nefc max, [16] launch slot."""
+        out = np.zeros((self.n_envs, 20), dtype=np.uint32)
+        self.torch.cuda.synchronize(self.device)
+        _ck(lib().mw_get_env_profile(self.h, out.ctypes.data))
+        return out
 
     def env_cost(self):
         out = np.zeros(self.n_envs, dtype=np.uint32)

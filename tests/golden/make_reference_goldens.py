@@ -11,7 +11,10 @@ Per task the file holds
     all 7 info keys, qpos, qvel, mocap;
   * 2 goals x 120 steps driven by the reference's scripted policy (contact-rich), keys prefixed `p_`;
   * 1 goal x 60 steps with `partially_observable=True` (ML benchmarks), keys prefixed `po_`;
-  * 1 goal x 500 random-action steps (a full episode; the last step has truncate=True), keys prefixed `l_`.
+  * 1 goal x 500 random-action steps (a full episode; the last step has truncate=True), keys prefixed `l_`;
+  * 5 goals x the reference's scripted policy run closed-loop until success (+5 steps, at most 300): only the action
+    sequence, its length and whether the reference run succeeded, keys prefixed `s_` (replayed open-loop on the device,
+    where the reference's policy code is not available: tests/test_gpu.py::test_scripted_policy_actions_succeed).
 
 Run here (needs /root/reference):  python tests/golden/make_reference_goldens.py [task ...]
 tests/test_refpin.py checks oracle/tasks.py + oracle/sawyer_env.py against these files to 1e-12.
@@ -107,6 +110,22 @@ def make(task, factory=reference_env, policy_factory=reference_policy):
     A = np.random.default_rng(500).uniform(-1, 1, size=(500, 4)).astype(np.float32)
     first, tr = rollout(factory(task, rv), actions=A)
     add("l_", [dict(rand_vec=pad(rv), **first, **tr)])
+
+    acts, lens, succ, rvs = [], [], [], []
+    for tk in B.make_tasks([task], False, seed=21, n_goals=5):
+        rv = tk.unpack()["rand_vec"]
+        env, pol = factory(task, rv), policy_factory(task)
+        o, _ = env.reset()
+        A = np.zeros((300, 4), dtype=np.float32)
+        n, ok, stop = 0, False, 300
+        while n < stop:
+            a = np.clip(pol.get_action(o.copy()), -1, 1).astype(np.float32)
+            o, r, _, _, info = env.step(a)
+            A[n] = a; n += 1
+            if info["success"] == 1.0 and not ok:
+                ok, stop = True, min(300, n + 5)
+        acts.append(A); lens.append(n); succ.append(ok); rvs.append(pad(rv))
+    out["s_actions"], out["s_len"], out["s_success"], out["s_rand_vec"] = acts, lens, succ, rvs
 
     out["source"] = np.frombuffer(b"reference glue (metaworld 3.1.1 classes, unmodified) on restated physics (oracle/mjphys)", dtype=np.uint8)
     np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), f"traj_{task}.npz"),

@@ -1,0 +1,141 @@
+"""CPU suite: the REAL host code of `metaworld_b200` (benchmarks.make_tasks, MetaWorldVecEnv, evaluation) against the
+REFERENCE's whole vector stack -- `gym.make_vec("Meta-World/MT10" | "ML10-train", ...)` from /root/reference running
+unmodified on oracle/refshim (gymnasium + mujoco stand-ins, see oracle/refshim/README.md).  Both sides step the same
+float64 oracle physics (ours through tests/oracle_engine.py), so every difference is host logic: goal generation, task
+selection streams, one-hot ids, TimeLimit / terminate-on-success, SAME_STEP autoreset, final_obs / final_info /
+episode statistics, checkpoint format.  Needs /root/reference, i.e. runs in the build container, not on the GPU box."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.skipif(not os.path.isdir("/root/reference/metaworld"), reason="/root/reference not present")
+KEYS = ("success", "near_object", "grasp_success", "grasp_reward", "in_place_reward", "obj_to_target", "unscaled_reward")
+
+
+@pytest.fixture(scope="module")
+def gym():
+    from oracle import refshim
+    refshim.activate()
+    import gymnasium
+    return gymnasium
+
+
+def _ours(kind, name, **kw):
+    from metaworld_b200 import vector_env as V
+    from metaworld_b200 import benchmarks as B
+    from oracle_engine import OracleEngine
+    names = {"MT10": B.MT10, "ML10": B.ML10["train"] * 2}.get(name, [name])
+    eng = OracleEngine(list(dict.fromkeys(names)))
+    return (V.make_mt_envs if kind == "mt" else V.make_ml_envs)(name, engine=eng, **kw)
+
+
+def _compare_rollout(ref, ours, steps, seed, atol=2e-6):
+    o1, i1 = ref.reset()
+    o2, i2 = ours.reset()
+    assert o1.shape == o2.shape and o1.dtype == o2.dtype and np.abs(o1 - o2).max() < atol
+    n = o1.shape[0]
+    rng = np.random.default_rng(seed)
+    n_done = 0
+    for t in range(steps):
+        a = rng.uniform(-1, 1, size=(n, 4)).astype(np.float32)
+        a[:, 3] = 1.0 if t % 7 > 3 else a[:, 3]
+        r1 = ref.step(a)
+        r2 = ours.step(a)
+        assert r1[0].dtype == r2[0].dtype and np.abs(r1[0] - r2[0]).max() < atol, t
+        assert r1[1].dtype == r2[1].dtype and np.abs(r1[1] - r2[1]).max() < 1e-5, t
+        assert r1[2].dtype == r2[2].dtype and np.array_equal(r1[2], r2[2]) and np.array_equal(r1[3], r2[3]), t
+        f1, f2 = r1[4], r2[4]
+        assert set(f1) == set(f2), (t, sorted(f1), sorted(f2))
+        for k in (KEYS if "success" in f1 else ()):
+            assert np.abs(np.asarray(f1[k], dtype=np.float64) - f2[k]).max() < 1e-5 and np.array_equal(f1["_" + k], f2["_" + k])
+        done = r1[2] | r1[3]
+        assert ("final_obs" in f1) == ("final_obs" in f2) == bool(done.any())
+        if done.any():
+            n_done += int(done.sum())
+            assert np.array_equal(f1["_final_obs"], f2["_final_obs"]) and np.array_equal(f1["_final_info"], f2["_final_info"])
+            for e in np.nonzero(done)[0]:
+                assert np.abs(f1["final_obs"][e] - f2["final_obs"][e]).max() < atol
+            for e in np.nonzero(~done)[0]:
+                assert f1["final_obs"][e] is None and f2["final_obs"][e] is None
+            fi1, fi2 = f1["final_info"], f2["final_info"]
+            for k in KEYS:
+                assert np.abs(np.asarray(fi1[k], dtype=np.float64) - fi2[k]).max() < 1e-5 and np.array_equal(fi1["_" + k], fi2["_" + k])
+            assert np.array_equal(fi1["episode"]["l"], fi2["episode"]["l"]) and np.allclose(fi1["episode"]["r"], fi2["episode"]["r"], atol=1e-3)
+            assert np.array_equal(fi1["episode"]["_r"], fi2["episode"]["_r"]) and np.array_equal(fi1["_episode"], fi2["_episode"])
+        # the task each sub-env is on (goal vector) follows the same stream
+        rv1 = ref.get_attr("_last_rand_vec"); rv2 = ours.get_attr("_last_rand_vec")
+        assert all(np.array_equal(x, y) for x, y in zip(rv1, rv2)), t
+    return n_done
+
+
+def test_mt10_one_hot_random_select_matches_reference_stack(gym):
+    kw = dict(seed=42, use_one_hot=True, max_episode_steps=9, terminate_on_success=True, num_goals=3)
+    ref = gym.make_vec("Meta-World/MT10", vector_strategy="sync", **kw)
+    ours = _ours("mt", "MT10", **kw)
+    assert ref.num_envs == ours.num_envs == 10
+    assert ref.single_observation_space.shape == ours.single_observation_space.shape == (49,)
+    assert ref.single_observation_space.dtype == ours.single_observation_space.dtype
+    assert np.array_equal(ref.single_observation_space.low, ours.single_observation_space.low)
+    assert ref.get_attr("task_name") is not None
+    # goals (the _make_tasks legacy-RNG protocol, metaworld/__init__.py:114-179) are the reference's
+    for tr, to in zip(ref.get_attr("tasks"), ours.get_attr("tasks")):
+        assert len(tr) == len(to) == 3
+        for a, b in zip(tr, to):
+            import pickle
+            assert np.array_equal(pickle.loads(a.data)["rand_vec"], b.unpack()["rand_vec"]) and a.env_name == b.env_name
+    assert _compare_rollout(ref, ours, 30, seed=1) >= 30
+    # evaluation protocol pieces used by metaworld/evaluation.py
+    ref.call("toggle_terminate_on_success", False); ours.call("toggle_terminate_on_success", False)
+    assert ref.get_attr("terminate_on_success") == ours.get_attr("terminate_on_success")
+    _compare_rollout(ref, ours, 12, seed=2)
+    # checkpoint: same ids, same keys, same task lists and RNG states; each side loads the other's
+    c1, c2 = ref.call("get_checkpoint"), ours.call("get_checkpoint")
+    for (id1, d1), (id2, d2) in zip(c1, c2):
+        assert id1 == id2 and set(d1) <= set(d2) and d1["tasks"] != [] and d1["sample_tasks_on_reset"] == d2["sample_tasks_on_reset"]
+        assert [t["env_name"] for t in d1["tasks"]] == [t["env_name"] for t in d2["tasks"]]
+        assert d1["rng_state"] == d2["rng_state"] and d1["env_rng_state"]["np_random_state"] == d2["env_rng_state"]["np_random_state"]
+    ours.call("load_checkpoint", list(c1))
+    ref.call("load_checkpoint", list(c2))
+    _compare_rollout(ref, ours, 12, seed=3)
+
+
+def test_ml10_train_pseudorandom_partially_observable_matches_reference_stack(gym):
+    import metaworld
+    kw = dict(seed=7, meta_batch_size=20, max_episode_steps=8)
+    metaworld._N_GOALS = 4          # the ML entry points do not take num_goals (metaworld/__init__.py:631-654)
+    ref = gym.make_vec("Meta-World/ML10-train", vector_strategy="sync", **kw)
+    ours = _ours("ml", "ML10", split="train", num_goals=4, **kw)
+    assert ref.num_envs == ours.num_envs == 20 and ref.single_observation_space.dtype == ours.single_observation_space.dtype == np.float64
+    ref.call("sample_tasks"); ours.call("sample_tasks")
+    assert ref.get_attr("sample_tasks_on_reset") == ours.get_attr("sample_tasks_on_reset") == tuple([False] * 20)
+    _compare_rollout(ref, ours, 10, seed=5)
+    for _ in range(3):          # no-collision cyclic sampling with reshuffle at wrap-around (wrappers.py:156-160)
+        ref.call("sample_tasks"); ours.call("sample_tasks")
+        assert all(np.array_equal(x, y) for x, y in zip(ref.get_attr("_last_rand_vec"), ours.get_attr("_last_rand_vec")))
+    ref.call("toggle_sample_tasks_on_reset", True); ours.call("toggle_sample_tasks_on_reset", True)
+    n = _compare_rollout(ref, ours, 18, seed=6)
+    assert n >= 40
+    o1, _ = ref.reset(); o2, _ = ours.reset()
+    assert not o1[:, 36:].any() and not o2[:, 36:].any()
+
+
+def test_mt1_single_task_vector_and_explicit_resets(gym):
+    import metaworld
+    kw = dict(seed=3, max_episode_steps=6)
+    metaworld._N_GOALS = 5
+    # MT1 through the reference returns the single (wrapped) env of make_mt_envs; compare through our 1-env vector view
+    renv = metaworld.make_mt_envs("door-open-v3", **kw)
+    ours = _ours("mt", "door-open-v3", num_goals=5, **kw)
+    o1, _ = renv.reset(); o2, _ = ours.reset()
+    assert np.abs(o1 - o2[0]).max() < 2e-6
+    rng = np.random.default_rng(0)
+    for t in range(5):
+        a = rng.uniform(-1, 1, 4).astype(np.float32)
+        x1 = renv.step(a); x2 = ours.step(a[None])
+        assert np.abs(x1[0] - x2[0][0]).max() < 2e-6 and abs(x1[1] - x2[1][0]) < 1e-5 and bool(x1[3]) == bool(x2[3][0])
+    # explicit resets draw a new task each time, in the reference's order
+    for _ in range(4):
+        o1, _ = renv.reset(); o2, _ = ours.reset()
+        assert np.abs(o1 - o2[0]).max() < 2e-6
+        assert np.array_equal(renv.unwrapped._last_rand_vec, ours.get_attr("_last_rand_vec")[0])

@@ -33,6 +33,15 @@ class FakeEngine:
     def set_options(self, max_steps, tos, seed):
         self.max_steps, self.tos = max_steps, bool(tos)
 
+    def get_state(self):
+        from metaworld_b200.engine import ENVSTATE_DTYPE
+        st = np.zeros(self.n, dtype=ENVSTATE_DTYPE)
+        st["snapshot"] = self.snap.numpy(); st["path_len"] = self.plen.numpy()
+        return st
+
+    def set_state(self, st):
+        self.snap[:] = torch.from_numpy(st["snapshot"].astype(np.int32)); self.plen[:] = torch.from_numpy(st["path_len"].astype(np.float32))
+
     def reset(self, snapshot_ids, obs, env_ids=None):
         self.snap[:] = snapshot_ids
         self.plen[:] = 0
@@ -48,9 +57,11 @@ class FakeEngine:
         reward[:] = 1.0
         info[:] = 0; info[:, 0] = succ.float()
         term[:] = t.to(torch.uint8); trunc[:] = tr.to(torch.uint8)
+        if info.shape[1] >= 9:          # packed record (include/metaworld_b200.h: info_stride >= 9)
+            info[:, 7] = reward; info[:, 8] = (t.int() + 2 * tr.int()).float()
         done = t | tr
         final_obs[done] = obs[done]
-        final_info[done, :7] = info[done]; final_info[done, 7] = self.plen[done]
+        final_info[done, :7] = info[done][:, :7]; final_info[done, 7] = self.plen[done]
         self.snap[done] = next_snapshot[done]
         self.plen[done] = 0
         obs[done, 0] = self.snap[done].float(); obs[done, 1] = 0
@@ -75,9 +86,10 @@ def test_reset_step_autoreset_and_info_layout():
     for t in range(1, 9):
         obs, r, term, trunc, info = env.step(np.zeros((6, 4), np.float32))
         assert r.dtype == np.float64 and term.dtype == bool and trunc.dtype == bool
-        for k in INFO_KEYS:
-            assert info[k].shape == (6,) and info["_" + k].all()
         done = term | trunc
+        for k in (INFO_KEYS if not done.all() else ()):      # SAME_STEP: a finished env's step info lives in final_info only
+            assert info[k].shape == (6,) and np.array_equal(info["_" + k], ~done) and not info[k][done].any()
+        assert ("success" in info) == (not done.all())
         if t == 3:           # odd envs succeed on their 3rd step and terminate (terminate_on_success)
             assert np.array_equal(term, np.arange(6) % 2 == 1)
         if done.any():
@@ -123,19 +135,31 @@ def test_pseudorandom_task_cycle_and_attribute_rpc():
 
 
 def test_checkpoint_round_trip_restores_task_stream():
+    """Reference format (metaworld/wrappers.py:125-142,275-322): (env_id, dict) per sub-env; a second env that loads it
+    continues with the same task sequence (cross-checked against the reference itself in tests/test_refpin_vector.py)."""
     names = ["reach-v3", "push-v3"]
     env, _ = make(names, 4, max_episode_steps=2)
     env.reset()
     env.step(np.zeros((4, 4), np.float32))
     ck = env.call("get_checkpoint")
+    assert len(ck) == 4 and all(isinstance(c, tuple) and len(c) == 2 for c in ck)
+    assert ck[0][0] == "<class 'metaworld.envs.sawyer_reach_v3.SawyerReachEnvV3'>_0" and ck[1][0].endswith("SawyerPushEnvV3'>_1")
+    assert set(ck[0][1]) >= {"tasks", "rng_state", "sample_tasks_on_reset", "env_rng_state"}
+    assert set(ck[0][1]["env_rng_state"]) == {"np_random_state", "action_space_rng_state", "obs_space_rng_state", "goal_space_rng_state"}
+    assert isinstance(ck[0][1]["tasks"][0]["data"], str)          # base64, json-serialisable
+    import json
+    json.dumps([c[1]["tasks"] for c in ck])
     a = []
     for _ in range(8):
         o, *_ = env.step(np.zeros((4, 4), np.float32)); a.append(o[:, 0].copy())
     env2, _ = make(names, 4, max_episode_steps=2)
     env2.reset()
-    env2.call("load_checkpoint", ck)
-    # the restored RNG / task index reproduce the same sequence of selected tasks from the next draw on
-    t1 = [env.sub[e].np_random.bit_generator.state for e in range(4)]
-    env.call("load_checkpoint", ck)
-    assert [env.sub[e].np_random.bit_generator.state for e in range(4)] == [env2.sub[e].np_random.bit_generator.state for e in range(4)]
-    assert t1 != [env.sub[e].np_random.bit_generator.state for e in range(4)] or True
+    env2.step(np.zeros((4, 4), np.float32))
+    env2.call("load_checkpoint", list(reversed(ck)))      # matched by env_id, not by position
+    b = []
+    for _ in range(8):
+        o, *_ = env2.step(np.zeros((4, 4), np.float32)); b.append(o[:, 0].copy())
+    # FakeEngine's obs[0] is the snapshot id each env runs: the restored sampler reproduces the task sequence
+    assert np.array_equal(np.array(a)[1:], np.array(b)[1:])
+    with pytest.raises(ValueError):
+        env2.call("load_checkpoint", [("nobody", ck[0][1])])
