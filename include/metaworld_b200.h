@@ -42,9 +42,13 @@ int mw_set_envs(mw_engine*, int n_envs, const int* env_model);
 /* Episode-start snapshots.  The reference's reset() = reset_model, mj_resetData, reset_model
  * (2 x 50 x 5 mj_step, metaworld/sawyer_xyz_env.py:664-695) is a pure function of (task, rand_vec,
  * partially_observable) because tasks freeze rand_vec (set_task, :298-318); it is evaluated once per
- * distinct goal by the same device physics and cached.  Appends n snapshots, returns their ids.   */
+ * distinct goal by the same device physics and cached.  Appends n snapshots, returns their ids.
+ * rand_vec_pass1 (NULL = same as rand_vec): with an UNFROZEN rand_vec (_make_tasks, the goal_hidden / goal_observable
+ * envs, metaworld/env_dict.py:144-152) each reset_model pass draws its own vector; the first pass's one survives in
+ * whatever the task's reset_model reads before the next kinematics update (e.g. the stale object pose in the reset obs). */
 int mw_build_snapshots(mw_engine*, int n, const int* model_idx, const float* rand_vec /*[n,6]*/,
-                       const unsigned char* partially_observable, int* snapshot_ids_out);
+                       const float* rand_vec_pass1 /*[n,6] or NULL*/, const unsigned char* partially_observable,
+                       int* snapshot_ids_out);
 /* Appends n snapshot records produced elsewhere (mw_get_snapshots of another engine, e.g. the float64 build of this
  * library, or a checkpoint); same record layout, ids returned like mw_build_snapshots.                           */
 int mw_append_snapshots(mw_engine*, int n, const void* records, int* snapshot_ids_out);
@@ -71,6 +75,20 @@ int mw_reset(mw_engine*, int n, const int* env_ids /*DEV or NULL*/, const int* s
 int mw_step(mw_engine*, const float* actions, float* obs, int obs_stride, float* reward,
             unsigned char* terminated, unsigned char* truncated, float* info, int info_stride, float* final_obs,
             float* final_info, const int* next_snapshot, void* stream);
+
+/* SawyerXYZEnv.evaluate_state(obs, action) (metaworld/sawyer_xyz_env.py:644-656 -> the task's evaluate_state /
+ * compute_reward): reward and info of every env's CURRENT physics state for caller-supplied observations and actions.
+ * One forward pass (poses, contact forces for touching_object), no state change.  actions DEV [n,4], obs DEV
+ * [n,obs_stride], out DEV [n,8] = the 7 info values then the reward.                                              */
+int mw_evaluate(mw_engine*, const float* actions, const float* obs, int obs_stride, float* out, void* stream);
+
+/* Per-env fault bits accumulated since the last call (host int[n_envs], cleared by the call; synchronises).  The kernel
+ * cannot raise where the reference does, so it clamps and flags:
+ *   1 MW_FAULT_TOL_BOUNDS  reward_utils.tolerance: lower > upper          (ValueError, reward_utils.py:124-125)
+ *   2 MW_FAULT_TOL_MARGIN  reward_utils.tolerance: margin < 0             (ValueError, reward_utils.py:134-135)
+ *   4 MW_FAULT_HAMACHER    hamacher_product input outside [0, 1]          (ValueError, reward_utils.py:237-238)
+ *   8 MW_FAULT_NONFINITE   non-finite observation or reward (the reference's `_did_see_sim_exception` path)      */
+int mw_get_faults(mw_engine*, int* out);
 
 /* options: max_episode_steps (TimeLimit), terminate_on_success (0/1), device sampler seed */
 int mw_set_options(mw_engine*, int max_episode_steps, int terminate_on_success, unsigned long long seed);

@@ -209,19 +209,41 @@ def make_tasks(env_names, partially_observable: bool, seed=None, n_goals=N_GOALS
     return tasks
 
 
+class EnvClass:
+    """Stands where the reference keeps an env CLASS (``benchmark.train_classes[name]``, metaworld/__init__.py:184-196):
+    calling it builds the bare single env over the engine (metaworld_b200.single_env.SawyerXYZEnvB200)."""
+
+    def __init__(self, env_name):
+        self.env_name = env_name
+        self.__name__ = REFERENCE_CLASS[env_name].rsplit(".", 1)[1]
+
+    def __call__(self, *a, **k):
+        from .single_env import SawyerXYZEnvB200
+        return SawyerXYZEnvB200(self.env_name, *a, **k)
+
+    def __repr__(self):
+        return f"<class '{REFERENCE_CLASS[self.env_name]}'>"
+
+
+def _classes(names):
+    from collections import OrderedDict
+    return OrderedDict((n, EnvClass(n)) for n in names)
+
+
 class Benchmark:
-    """``metaworld.Benchmark`` surface: train_classes / test_classes (name lists) and train_tasks / test_tasks."""
+    """``metaworld.Benchmark`` surface: train_classes / test_classes (OrderedDict name -> env class, iterates as the
+    names) and train_tasks / test_tasks."""
 
     def __init__(self, train, test, partially_observable, seed, test_seed=None, n_goals=N_GOALS):
-        self.train_classes = list(train)
-        self.test_classes = list(test)
+        self.train_classes = _classes(train)
+        self.test_classes = _classes(test)
         self.train_tasks = make_tasks(train, partially_observable, seed, n_goals)
         self.test_tasks = make_tasks(test, partially_observable, seed if test_seed is None else test_seed, n_goals) if test else []
 
 
 def MT1(env_name, seed=None, n_goals=N_GOALS):
     b = Benchmark([env_name], [], False, seed, n_goals=n_goals)
-    b.test_classes = [env_name]
+    b.test_classes = _classes([env_name])
     return b
 
 

@@ -20,8 +20,8 @@ enum { G_PLANE = 0, G_HFIELD, G_SPHERE, G_CAPSULE, G_ELLIPSOID, G_CYLINDER, G_BO
 
 struct RawCon { creal dist, pos[3], normal[3]; };
 
-struct DShape {
-  int type; creal pos[3]; creal mat[9]; creal size[3]; const float4* vert; int nvert;   // hull vertices packed xyz_ (16-byte loads)
+struct DShape {   // pos / mat point at the geom's world pose (shared memory in the kernel): nothing is copied into the thread's stack
+  int type; const creal* pos; const creal* mat; creal size[3]; const float4* vert; int nvert;   // hull vertices packed xyz_ (16-byte loads)
 };
 
 // ------------------------------------------------------------------ plane pairs

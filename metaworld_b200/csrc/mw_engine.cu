@@ -34,7 +34,7 @@ struct EngineDev {
   const float* const* meshverts;                     // [n_models] device pointers
   MwEnvState* state; MwSnapshot* snaps;
   const int* goal_first; const int* goal_count;      // device sampler ranges (may be NULL)
-  int* diag;                                         // [n_envs][2]: contacts dropped, solver iterations
+  int* diag;                                         // [n_envs][3]: contacts dropped, solver iterations, MW_FAULT_* bits (OR)
   EpaWs* epa;                                        // GJK/EPA polytope workspace, one per launched warp (global memory)
   unsigned long long* prof;                          // [16] summed cycle / event counters (mw_get_profile)
   unsigned long long* model_cycles;                  // [n_models][2]: warp cycles, env steps (drives mw_rebalance)
@@ -47,6 +47,7 @@ struct EngineDev {
 struct BlockShared {
   alignas(16) unsigned char model[(sizeof(MwModel) + 15) / 16 * 16];
   MwTaskConst tc;
+  CtaShare cs;
   alignas(8) unsigned long long bar;
 };
 struct WarpShared {
@@ -77,7 +78,12 @@ DEV void stage_model(BlockShared* bs, const unsigned char* src, unsigned bytes, 
   __syncthreads();
 }
 
-struct Eng { const MwModel* m; const float* meshvert; };
+// wires a warp into its CTA's convex-pair queue (mw_physics.cuh: CtaShare); visible to the other warps after the first PHASE_SYNC
+DEV void join_cta(BlockShared* bs, WarpShared* wsa, WarpScratch* w, int warp, int live_warps) {
+  if (threadIdx.x == 0) { bs->cs.q_head = 0; bs->cs.nwarp = live_warps; bs->cs.peer_stride = (int)sizeof(WarpShared); bs->cs.peer0 = (unsigned char*)wsa; }
+  if ((threadIdx.x & 31) == 0) { w->cta = &bs->cs; w->warp_in_cta = warp; w->ncand = 0; }
+  __syncwarp();
+}
 __device__ void eng_forward(const TaskCtx& c, int lane) { mw_forward(c.m, c.meshvert, c.w, lane); }
 __device__ void eng_sim(const TaskCtx& c, int nstep, int lane) {
   for (int s = 0; s < nstep; s++) { mw_forward(c.m, c.meshvert, c.w, lane); mw_euler(c.m, c.w, lane); }
@@ -146,10 +152,12 @@ k_step(EngineDev e, const int* __restrict__ block_order, const int* __restrict__
   WarpShared* ws = wsa + warp;
   ws->w.epa = e.epa + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp);
   WarpScratch* w = &ws->w;
+  join_cta(bs, wsa, w, warp, block_count[blk]);
   const MwModel* m = (const MwModel*)bs->model;
   load_env(ws, e.state + env, lane);
   if (lane < 16) w->prof[lane] = 0;
-  const long long t_begin = clock64();
+  if (lane == 0) w->fault = 0;
+  const long long t_begin = mw_clock();
   real act[4];
   for (int i = 0; i < 4; i++) act[i] = fmin(fmax((real)actions[4 * env + i], (real)-1), (real)1);
   TaskCtx c; c.m = m; c.tc = &bs->tc; c.w = w; c.s = &ws->es; c.action = act; c.meshvert = e.meshverts[mi];
@@ -166,7 +174,7 @@ k_step(EngineDev e, const int* __restrict__ block_order, const int* __restrict__
   mw_forward(m, c.meshvert, w, lane);
   iters += w->solver_iter; dropped += w->ncon_dropped; ncon_max = max(ncon_max, w->ncon); nefc_max = max(nefc_max, w->nefc);
   bool done = false;
-  const long long t_phys = clock64();
+  const long long t_phys = mw_clock();
   if (lane == 0) {
     ws->es.path_len += 1.f;
     task_live_update(c);
@@ -183,12 +191,16 @@ k_step(EngineDev e, const int* __restrict__ block_order, const int* __restrict__
     reward[env] = (float)rew; terminated[env] = term; truncated[env] = trunc;
     if (info_stride >= 9) { info_out[(size_t)env * info_stride + 7] = (float)rew; info_out[(size_t)env * info_stride + 8] = (float)((int)term + 2 * (int)trunc); }   // packed record: one D2H copy
     ws->info[7] = (term || trunc) ? 1.f : 0.f;
-    e.diag[2 * env] += dropped; e.diag[2 * env + 1] += iters;
-    w->prof[7] = clock64() - t_phys; w->prof[8] = clock64() - t_begin;
-    // launch-order key: this env's OWN work.  (The whole-step time is the same for all warps of a CTA -- they wait for
-    // each other at every phase boundary -- and would keep light envs glued to the heavy one they were once grouped with.)
+    { bool fin = isfinite((float)rew); for (int i = 0; i < 39; i++) fin = fin && isfinite(ws->obs[i]); if (!fin) w->fault |= MW_FAULT_NONFINITE; }
+    e.diag[3 * env] += dropped; e.diag[3 * env + 1] += iters; e.diag[3 * env + 2] |= w->fault;
+    w->prof[7] = mw_clock() - t_phys; w->prof[8] = mw_clock() - t_begin;
+    // launch-order key: the cycles this env spent in its constraint solver + constraint assembly.  The whole-step time
+    // is the same for all warps of a CTA (they wait for each other at every phase boundary) and would keep light envs
+    // glued to the heavy one they were once grouped with; the collision phase is shared across the CTA (CtaShare); the
+    // other phases cost the same for every env of a model.  What is left to group by is the solver.
     const long long own = w->prof[8] - w->prof[12];
-    e.env_cost[env] = (unsigned)(own > 0xFFFFFFFFll ? 0xFFFFFFFFll : own);
+    const long long key = w->prof[5] + w->prof[3];
+    e.env_cost[env] = (unsigned)(key > 0xFFFFFFFFll ? 0xFFFFFFFFll : key);
     w->prof[6] = own - w->prof[7] - (w->prof[0] + w->prof[1] + w->prof[3] + w->prof[4] + w->prof[5]);   // euler + glue
   }
   SYNCW();
@@ -234,7 +246,7 @@ k_step(EngineDev e, const int* __restrict__ block_order, const int* __restrict__
 // builds episode-start snapshots: exact reset() sequence of the reference (reset_model, mj_resetData, reset_model)
 __global__ void __launch_bounds__(BLOCK_THREADS, 1)
 k_snapshot(EngineDev e, const int* __restrict__ block_model, const int* __restrict__ block_start, const int* __restrict__ block_count,
-           const int* __restrict__ perm, const float* __restrict__ rand_vec, const unsigned char* __restrict__ partial, int snap_base) {
+           const int* __restrict__ perm, const float* __restrict__ rand_vec, const float* __restrict__ rand_vec_pass1, const unsigned char* __restrict__ partial, int snap_base) {
   extern __shared__ __align__(16) unsigned char smem[];
   BlockShared* bs = (BlockShared*)smem;
   WarpShared* wsa = (WarpShared*)(smem + sizeof(BlockShared));
@@ -246,8 +258,10 @@ k_snapshot(EngineDev e, const int* __restrict__ block_model, const int* __restri
   WarpShared* ws = wsa + warp;
   ws->w.epa = e.epa + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp);
   WarpScratch* w = &ws->w;
+  join_cta(bs, wsa, w, warp, block_count[blockIdx.x]);
   const MwModel* m = (const MwModel*)bs->model;
-  const float* rv = rand_vec + 6 * item;
+  const float* rv2 = rand_vec + 6 * item;
+  const float* rv1 = rand_vec_pass1 ? rand_vec_pass1 + 6 * item : rv2;   // an unfrozen rand_vec draws once per reset_model pass
   real act[4] = {0, 0, 0, 0};
   TaskCtx c; c.m = m; c.tc = &bs->tc; c.w = w; c.s = &ws->es; c.action = act; c.meshvert = e.meshverts[mi];
   for (int i = lane; i < 128; i += 32) ((float*)&ws->es)[i] = 0.f;
@@ -272,7 +286,7 @@ k_snapshot(EngineDev e, const int* __restrict__ block_model, const int* __restri
     }
     if (lane == 0) { real t[3]; tcp_center(c, t); for (int i = 0; i < 3; i++) ws->es.init_tcp[i] = (float)t[i]; }
     SYNCW();
-    task_reset_model(c, rv, lane);
+    task_reset_model(c, pass == 0 ? rv1 : rv2, lane);
     SYNCW();
   }
   if (lane == 0) {
@@ -314,6 +328,7 @@ k_substeps(EngineDev e, const int* __restrict__ block_model, const int* __restri
   const int env = perm[block_start[blockIdx.x] + warp];
   WarpShared* ws = wsa + warp;
   ws->w.epa = e.epa + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp);
+  join_cta(bs, wsa, &ws->w, warp, block_count[blockIdx.x]);
   const MwModel* m = (const MwModel*)bs->model;
   load_env(ws, e.state + env, lane);
   if (lane == 0) { ws->w.ctrl[0] = c0; ws->w.ctrl[1] = c1; }
@@ -335,6 +350,42 @@ k_substeps(EngineDev e, const int* __restrict__ block_model, const int* __restri
     return;
   }
   store_env(ws, e.state + env, lane);
+}
+
+// evaluate_state (sawyer_xyz_env.py:644-656 + the task's compute_reward): reward / info of the CURRENT state for a given
+// (obs, action); one forward pass to rebuild poses and contact forces, nothing is written back to the state
+__global__ void __launch_bounds__(BLOCK_THREADS, 1)
+k_evaluate(EngineDev e, const int* __restrict__ block_model, const int* __restrict__ block_start, const int* __restrict__ block_count,
+           const int* __restrict__ perm, const float* __restrict__ actions, const float* __restrict__ obs_in, int obs_stride, float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  BlockShared* bs = (BlockShared*)smem;
+  WarpShared* wsa = (WarpShared*)(smem + sizeof(BlockShared));
+  const int mi = block_model[blockIdx.x];
+  stage_model(bs, e.models + (size_t)mi * e.model_stride, (unsigned)sizeof(bs->model), e.taskconsts + mi);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= block_count[blockIdx.x]) return;
+  const int env = perm[block_start[blockIdx.x] + warp];
+  WarpShared* ws = wsa + warp;
+  ws->w.epa = e.epa + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp);
+  WarpScratch* w = &ws->w;
+  join_cta(bs, wsa, w, warp, block_count[blockIdx.x]);
+  const MwModel* m = (const MwModel*)bs->model;
+  load_env(ws, e.state + env, lane);
+  if (lane < 16) w->prof[lane] = 0;
+  if (lane == 0) { w->fault = 0; w->ctrl[0] = actions[4 * env + 3]; w->ctrl[1] = -actions[4 * env + 3]; }
+  SYNCW();
+  mw_forward(m, e.meshverts[mi], w, lane);
+  if (lane == 0) {
+    real raw_act[4]; for (int i = 0; i < 4; i++) raw_act[i] = actions[4 * env + i];
+    TaskCtx c; c.m = m; c.tc = &bs->tc; c.w = w; c.s = &ws->es; c.action = raw_act; c.meshvert = e.meshverts[mi];
+    task_live_update(c);
+    real obsr[39]; for (int i = 0; i < 39; i++) obsr[i] = obs_in[(size_t)env * obs_stride + i];
+    real rew, inf[INFO_N];
+    task_reward(c, obsr, &rew, inf);
+    for (int i = 0; i < INFO_N; i++) out[8 * env + i] = (float)inf[i];
+    out[8 * env + 7] = (float)rew;
+    e.diag[3 * env + 2] |= w->fault;
+  }
 }
 
 // ---------------------------------------------------------------- launch-order maintenance
@@ -393,6 +444,7 @@ struct mw_engine {
   EpaWs* d_epa = nullptr; size_t epa_cap = 0;
   unsigned long long* d_prof = nullptr; unsigned long long* d_model_cycles = nullptr; unsigned* d_env_prof = nullptr; int profiling = 0;
   unsigned* d_env_cost = nullptr; int *d_block_order = nullptr, *d_model_first = nullptr, *d_model_count = nullptr; int n_sorted_models = 0;
+  std::vector<int> h_faults;                                   // fault bits already drained from d_diag by mw_get_counters
   std::vector<int> env_model; std::vector<int> model_order;   // block table inputs (mw_rebalance re-sorts the models by measured cost)
   // env block table
   int n_blocks = 0; int *d_block_model = nullptr, *d_block_start = nullptr, *d_block_count = nullptr, *d_perm = nullptr;
@@ -506,6 +558,7 @@ int mw_create(mw_engine** out, int device, int n_models, const void* models, con
   CK(cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
   CK(cudaFuncSetAttribute(k_snapshot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
   CK(cudaFuncSetAttribute(k_substeps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+  CK(cudaFuncSetAttribute(k_evaluate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
   *out = E;
   return MW_OK;
 }
@@ -527,6 +580,7 @@ int mw_set_envs(mw_engine* E, int n_envs, const int* env_model) {
   for (int v : im) if (v < 0 || v >= E->n_models) return fail(MW_ERR_ARG, "mw_set_envs: model index out of range");
   E->env_model = im;
   E->n_envs = n_envs;
+  E->h_faults.assign(n_envs, 0);
   if (upload_env_blocks(E)) return MW_ERR_CUDA;
   if (E->d_env_cost) cudaFree(E->d_env_cost);
   CK(cudaMalloc((void**)&E->d_env_cost, sizeof(unsigned) * n_envs));
@@ -537,12 +591,12 @@ int mw_set_envs(mw_engine* E, int n_envs, const int* env_model) {
   if (E->d_env_prof) { cudaFree(E->d_env_prof); E->d_env_prof = nullptr; }
   if (E->profiling) { CK(cudaMalloc((void**)&E->d_env_prof, sizeof(unsigned) * MW_ENVPROF_W * n_envs)); CK(cudaMemset(E->d_env_prof, 0, sizeof(unsigned) * MW_ENVPROF_W * n_envs)); }
   if (E->d_diag) cudaFree(E->d_diag);
-  CK(cudaMalloc((void**)&E->d_diag, sizeof(int) * 2 * n_envs));
-  CK(cudaMemset(E->d_diag, 0, sizeof(int) * 2 * n_envs));
+  CK(cudaMalloc((void**)&E->d_diag, sizeof(int) * 3 * n_envs));
+  CK(cudaMemset(E->d_diag, 0, sizeof(int) * 3 * n_envs));
   return MW_OK;
 }
 
-int mw_build_snapshots(mw_engine* E, int n, const int* model_idx, const float* rand_vec, const unsigned char* partial, int* ids_out) {
+int mw_build_snapshots(mw_engine* E, int n, const int* model_idx, const float* rand_vec, const float* rand_vec_pass1, const unsigned char* partial, int* ids_out) {
   if (!E || n <= 0 || !model_idx || !rand_vec || !partial) return fail(MW_ERR_ARG, "mw_build_snapshots: bad arguments");
   CK(cudaSetDevice(E->device));
   if (E->n_snaps + n > E->snap_cap) {
@@ -560,10 +614,12 @@ int mw_build_snapshots(mw_engine* E, int n, const int* model_idx, const float* r
   if (upload(&d_bm, bm) || upload(&d_bs, bs) || upload(&d_bc, bc) || upload(&d_perm, perm)) return MW_ERR_CUDA;
   CK(cudaMalloc((void**)&d_rv, sizeof(float) * 6 * n)); CK(cudaMemcpy(d_rv, rand_vec, sizeof(float) * 6 * n, cudaMemcpyHostToDevice));
   CK(cudaMalloc((void**)&d_po, n)); CK(cudaMemcpy(d_po, partial, n, cudaMemcpyHostToDevice));
-  k_snapshot<<<(int)bm.size(), BLOCK_THREADS, smem_bytes()>>>(E->dev(), d_bm, d_bs, d_bc, d_perm, d_rv, d_po, E->n_snaps);
+  float* d_rv1 = nullptr;
+  if (rand_vec_pass1) { CK(cudaMalloc((void**)&d_rv1, sizeof(float) * 6 * n)); CK(cudaMemcpy(d_rv1, rand_vec_pass1, sizeof(float) * 6 * n, cudaMemcpyHostToDevice)); }
+  k_snapshot<<<(int)bm.size(), BLOCK_THREADS, smem_bytes()>>>(E->dev(), d_bm, d_bs, d_bc, d_perm, d_rv, d_rv1, d_po, E->n_snaps);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
-  cudaFree(d_bm); cudaFree(d_bs); cudaFree(d_bc); cudaFree(d_perm); cudaFree(d_rv); cudaFree(d_po);
+  cudaFree(d_bm); cudaFree(d_bs); cudaFree(d_bc); cudaFree(d_perm); cudaFree(d_rv); cudaFree(d_rv1); cudaFree(d_po);
   if (ids_out) for (int i = 0; i < n; i++) ids_out[i] = E->n_snaps + i;
   E->n_snaps += n; E->launches++;
   return MW_OK;
@@ -621,6 +677,25 @@ int mw_step(mw_engine* E, const float* actions, float* obs, int obs_stride, floa
   return MW_OK;
 }
 
+int mw_evaluate(mw_engine* E, const float* actions, const float* obs, int obs_stride, float* out, void* stream) {
+  if (!E || !E->d_state || !actions || !obs || !out || obs_stride < 39) return fail(MW_ERR_ARG, "mw_evaluate: bad arguments");
+  CK(cudaSetDevice(E->device));
+  k_evaluate<<<E->n_blocks, BLOCK_THREADS, smem_bytes(), (cudaStream_t)stream>>>(E->dev(), E->d_block_model, E->d_block_start, E->d_block_count, E->d_perm, actions, obs, obs_stride, out);
+  CK(cudaGetLastError());
+  E->launches++;
+  return MW_OK;
+}
+
+int mw_get_faults(mw_engine* E, int* out) {
+  if (!E || !out || !E->d_diag) return fail(MW_ERR_ARG, "mw_get_faults");
+  CK(cudaSetDevice(E->device));
+  std::vector<int> diag(3 * (size_t)E->n_envs);
+  CK(cudaMemcpy(diag.data(), E->d_diag, sizeof(int) * diag.size(), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < E->n_envs; i++) { out[i] = E->h_faults[i] | diag[3 * i + 2]; E->h_faults[i] = 0; diag[3 * i + 2] = 0; }
+  CK(cudaMemcpy(E->d_diag, diag.data(), sizeof(int) * diag.size(), cudaMemcpyHostToDevice));
+  return MW_OK;
+}
+
 int mw_set_options(mw_engine* E, int max_episode_steps, int terminate_on_success, unsigned long long seed) {
   if (!E || max_episode_steps <= 0) return fail(MW_ERR_ARG, "mw_set_options: bad arguments");
   E->max_steps = max_episode_steps; E->terminate_on_success = terminate_on_success; E->seed = seed;
@@ -665,10 +740,14 @@ int mw_debug_dump_floats(void) { return MW_MAXCON * 12 + MW_MAXDOF + 4; }
 int mw_get_counters(mw_engine* E, unsigned long long* out5) {
   if (!E || !out5) return fail(MW_ERR_ARG, "mw_get_counters");
   CK(cudaSetDevice(E->device));
-  std::vector<int> diag(2 * (size_t)(E->n_envs > 0 ? E->n_envs : 0));
-  if (E->n_envs) { CK(cudaMemcpy(diag.data(), E->d_diag, sizeof(int) * diag.size(), cudaMemcpyDeviceToHost)); CK(cudaMemset(E->d_diag, 0, sizeof(int) * diag.size())); }
+  std::vector<int> diag(3 * (size_t)(E->n_envs > 0 ? E->n_envs : 0));
+  if (E->n_envs) {
+    CK(cudaMemcpy(diag.data(), E->d_diag, sizeof(int) * diag.size(), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < E->n_envs; i++) { E->h_faults[i] |= diag[3 * i + 2]; }
+    CK(cudaMemset(E->d_diag, 0, sizeof(int) * diag.size()));
+  }
   unsigned long long dropped = 0, iters = 0;
-  for (int i = 0; i < E->n_envs; i++) { dropped += diag[2 * i]; iters += diag[2 * i + 1]; }
+  for (int i = 0; i < E->n_envs; i++) { dropped += diag[3 * i]; iters += diag[3 * i + 1]; }
   out5[0] = E->launches; out5[1] = E->env_steps; out5[2] = dropped; out5[3] = iters; out5[4] = E->env_steps * 6ull;
   E->launches = 0; E->env_steps = 0;
   return MW_OK;

@@ -21,6 +21,8 @@
 
 enum { JT_FREE = 0, JT_BALL, JT_SLIDE, JT_HINGE };
 
+struct ConvRes { RawCon r; int hit, pad; };   // result slot of one convex candidate pair (written by whichever warp of the CTA processed it)
+
 struct Contact {
   real pos[3], frame[9], dist, mu, fr1, fr3;
   real H[10];              // packed symmetric dim x dim cone Hessian (row-major upper)
@@ -31,8 +33,14 @@ struct Contact {
 
 // region U is time-shared: (a) geom world poses + EPA workspace during collision, (b) efc_J afterwards
 #define MW_UWORDS_J (MW_MAXEFC * NVP)
-#define MW_UWORDS_C (MW_MAXGEOM * 12 * 2 + (int)(sizeof(EpaSm) / 4) + 2)   // geom world poses (creal) + EPA scratch during collision
+#define MW_UWORDS_C (MW_MAXGEOM * 12 * 2 + (int)(sizeof(EpaSm) / 4) + 2 + MW_MAXCAND * (int)(sizeof(ConvRes) / 4))   // geom world poses (creal) + EPA scratch + convex-pair results during collision
 #define MW_UWORDS (MW_UWORDS_J > MW_UWORDS_C ? MW_UWORDS_J : MW_UWORDS_C)
+
+// CTA-wide sharing of the general convex pairs (GJK/EPA): every warp publishes its env's candidate pairs, then all warps
+// of the CTA pull (env, pair) items from one queue, so one env with many penetrating mesh pairs does not hold up its CTA
+// (and the kernel: the slowest env's collision phase was the critical path of the whole step).
+#define MW_MAXCAND 48
+struct CtaShare { int q_head, nwarp, peer_stride, pad; unsigned char* peer0; int q_cnt[16]; };
 
 struct WarpScratch {
   real lpos[MW_MAXLINK][3], lquat[MW_MAXLINK][4], lmat[MW_MAXLINK][9];
@@ -49,12 +57,17 @@ struct WarpScratch {
   EpaWs* epa;               // this warp's GJK/EPA polytope workspace (global memory, see mw_engine.cu)
   real eD[MW_MAXEFC], eAref[MW_MAXEFC], eJar[MW_MAXEFC], eJv[MW_MAXEFC], eF[MW_MAXEFC], eHd[MW_MAXSCALAR];
   Contact con[MW_MAXCON];
-  unsigned short cand[64];
+  unsigned short cand[MW_MAXCAND];   // this env's general convex candidate pairs of the current pass (pair indices)
+  CtaShare* cta; int warp_in_cta, ncand, pad_;
   int ncon, nefc, nscalar, nweld, solver_iter, ncon_dropped;
+  int fault;                // MW_FAULT_* bits raised by the task code during this step (lane 0)
   long long prof[16];       // cycle / event counters of this step (mw_get_profile order; [12] = cycles spent waiting in PHASE_SYNC; lane 0 only)
 };
 
 #define SYNCW() __syncwarp()
+// cycle counter that the compiler may not move across barriers / memory operations (plain clock64() was hoisted above
+// __syncthreads(), which booked every barrier wait on the phase that follows it)
+DEV long long mw_clock() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory"); return t; }
 #define QSET(w, i, v) { (w)->qposd[i] = (double)(v); (w)->qpos[i] = (real)(w)->qposd[i]; }   /* write a generalized position */
 
 // ------------------------------------------------------------------ kinematics  [MuJoCo mj_kinematics]
@@ -310,8 +323,8 @@ __device__ __noinline__ real mw_rne_bias(const MwModel* __restrict__ m, WarpScra
 // ------------------------------------------------------------------ collision  [MuJoCo mj_collision]
 DEV void mw_load_shape(const MwModel* m, const creal* gpose, const float* meshvert, int g, DShape* s) {
   s->type = m->geom_type[g];
-  for (int i = 0; i < 3; i++) { s->pos[i] = gpose[12 * g + i]; s->size[i] = m->geom_size[g][i]; }
-  for (int i = 0; i < 9; i++) s->mat[i] = gpose[12 * g + 3 + i];
+  s->pos = gpose + 12 * g; s->mat = gpose + 12 * g + 3;
+  for (int i = 0; i < 3; i++) s->size[i] = m->geom_size[g][i];
   s->vert = (const float4*)meshvert + m->geom_meshadr[g]; s->nvert = m->geom_meshnum[g];
 }
 DEV void make_frame(creal* fr) {
@@ -363,7 +376,7 @@ __device__ __noinline__ void mw_collide(const MwModel* __restrict__ m, const flo
   }
   if (lane == 0) { w->ncon = 0; w->ncon_dropped = 0; }
   SYNCW();
-  int ncon = 0;
+  int ncon = 0, ncand = 0, nover = 0;
   for (int base = 0; base < np; base += 32) {
     int p = base + lane;
     // ---- broadphase cull (conservative: never removes a pair that is within margin)
@@ -415,13 +428,35 @@ __device__ __noinline__ void mw_collide(const MwModel* __restrict__ m, const flo
     int start = ncon + incl - cnt;
     for (int k = 0; k < cnt; k++) if (start + k < MW_MAXCON) mw_store_contact(m, w, start + k, rc[k], p);
     ncon += __shfl_sync(FULLMASK, incl, 31);
-    // ---- general convex pairs: the whole warp works on one pair at a time
+    // ---- general convex pairs (cylinder / mesh): deferred to the CTA-wide queue below
     unsigned cm = __ballot_sync(FULLMASK, keep && !analytic);
     while (cm) {
       int src = __ffs(cm) - 1; cm &= cm - 1;
-      int pp = base + src;
+      if (ncand < MW_MAXCAND) { if (lane == 0) w->cand[ncand] = (unsigned short)(base + src); ncand++; }
+      else nover++;
+    }
+  }
+  ConvRes* cres = (ConvRes*)((unsigned char*)esm + sizeof(EpaSm));
+  CtaShare* cs = w->cta;
+  if (lane == 0) { w->ncand = ncand; cs->q_cnt[w->warp_in_cta] = ncand; }
+  if (threadIdx.x == 0) cs->q_head = 0;
+  __syncthreads();                       // candidates of all envs of the CTA are published
+  {
+    const int nw = cs->nwarp;
+    int total = 0; for (int o = 0; o < nw; o++) total += cs->q_cnt[o];
+    for (;;) {
+      int item = 0;
+      if (lane == 0) item = atomicAdd(&cs->q_head, 1);
+      item = __shfl_sync(FULLMASK, item, 0);
+      if (item >= total) break;
+      int o = 0, k = item;
+      while (k >= cs->q_cnt[o]) { k -= cs->q_cnt[o]; o++; }
+      WarpScratch* ow = (WarpScratch*)(cs->peer0 + (size_t)o * cs->peer_stride);     // the env this pair belongs to (same model: same CTA)
+      const creal* ogpose = (const creal*)ow->U;
+      ConvRes* ores = (ConvRes*)((unsigned char*)ogpose + MW_MAXGEOM * 12 * sizeof(creal) + sizeof(EpaSm));
+      const int pp = ow->cand[k];
       int h1 = m->pair_g1[pp], h2 = m->pair_g2[pp];
-      DShape a, b; mw_load_shape(m, gpose, meshvert, h1, &a); mw_load_shape(m, gpose, meshvert, h2, &b);
+      DShape a, b; mw_load_shape(m, ogpose, meshvert, h1, &a); mw_load_shape(m, ogpose, meshvert, h2, &b);
       creal mg = m->param[m->pair_param[pp]][0];
       RawCon r1; int c1;
       if (a.type == G_PLANE) {   // plane - mesh: support vertex against the plane
@@ -430,12 +465,16 @@ __device__ __noinline__ void mw_collide(const MwModel* __restrict__ m, const flo
         v3sub(t, sp, a.pos);
         r1.dist = v3dot(t, n); v3copy(r1.normal, n); v3addscl(r1.pos, sp, n, -(creal)0.5 * r1.dist);
         c1 = r1.dist <= mg;
-      } else { long long tc = clock64(); c1 = convex_pair(a, b, mg, &r1, esm, epa, lane, w->prof); if (lane == 0) { w->prof[2] += clock64() - tc; w->prof[9] += 1; } }
-      if (c1) { if (ncon < MW_MAXCON && lane == 0) mw_store_contact(m, w, ncon, r1, pp); ncon++; }
+      } else { long long tc = mw_clock(); c1 = convex_pair(a, b, mg, &r1, esm, epa, lane, w->prof); if (lane == 0) { w->prof[2] += mw_clock() - tc; w->prof[9] += 1; } }
+      if (lane == 0) { ores[k].hit = c1; if (c1) ores[k].r = r1; }
     }
   }
+  __syncthreads();                       // all results are in their owners' slots
+  for (int k = 0; k < ncand; k++) {      // in pair order: the contact list is a pure function of the state
+    if (cres[k].hit) { if (ncon < MW_MAXCON && lane == 0) mw_store_contact(m, w, ncon, cres[k].r, w->cand[k]); ncon++; }
+  }
   SYNCW();
-  if (lane == 0) { w->ncon = ncon < MW_MAXCON ? ncon : MW_MAXCON; w->ncon_dropped = ncon > MW_MAXCON ? ncon - MW_MAXCON : 0; }
+  if (lane == 0) { w->ncon = ncon < MW_MAXCON ? ncon : MW_MAXCON; w->ncon_dropped = (ncon > MW_MAXCON ? ncon - MW_MAXCON : 0) + nover; }
   SYNCW();
 }
 
@@ -562,8 +601,9 @@ __device__ __noinline__ void mw_make_constraints(const MwModel* __restrict__ m, 
     (void)rot;
     real R1 = R0 / m->impratio;
     con->mu = con->fr1 * sqrt(R1 / R0);
-    real Rk[4] = {R0, R1, R1, R1 * con->fr1 * con->fr1 / (con->fr3 * con->fr3)};
-    for (int k = 0; k < dim; k++) {
+    const real Rk[4] = {R0, R1, R1, R1 * con->fr1 * con->fr1 / (con->fr3 * con->fr3)};
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (k < dim) {
       real vel = 0; for (int d = 0; d < nv; d++) vel += J[(r0 + k) * NVP + d] * w->qvel[d];
       w->eD[r0 + k] = 1 / Rk[k];
       w->eAref[r0 + k] = k == 0 ? (-rp.B * vel - rp.K * rp.imp * (con->dist - incl)) : (-rf.B * vel);
@@ -581,26 +621,39 @@ DEV real mw_scalar_row(const WarpScratch* w, int r, real x, real* f, real* hd) {
   *f = active ? -D * x : (real)0; *hd = active ? D : (real)0;
   return active ? (real)0.5 * D * x * x : (real)0;
 }
-// elliptic cone block; x[0..dim) ; optionally forces and packed Hessian
+// elliptic cone block; x[0..dim) ; optionally forces and packed Hessian.  All loops run to the fixed bound 4 with a
+// `k < dim` guard and are fully unrolled: the small arrays then live in registers instead of the thread's local-memory
+// stack (dynamically indexed arrays were the bulk of the kernel's 5.9 K LDL/STL instructions and of its DRAM traffic).
 DEV real mw_cone(const WarpScratch* w, const Contact* con, const real* x, real* f, real* Hc, int* zone) {
   const int r0 = con->row, dim = con->dim;
   const real mu = con->mu;
-  real fr[4] = {0, con->fr1, con->fr1, con->fr3}, u[4] = {0, 0, 0, 0};
+  const real fr[4] = {0, con->fr1, con->fr1, con->fr3};
+  real u[4] = {0, 0, 0, 0};
   real N = x[0] * mu, T2 = 0;
-  for (int k = 1; k < dim; k++) { u[k] = x[k] * fr[k]; T2 += u[k] * u[k]; }
+#pragma unroll
+  for (int k = 1; k < 4; k++) if (k < dim) { u[k] = x[k] * fr[k]; T2 += u[k] * u[k]; }
   real T = sqrt(T2), cost = 0;
-  if (Hc) for (int i = 0; i < 10; i++) Hc[i] = 0;
+  if (Hc) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) Hc[i] = 0;
+  }
   if (N >= mu * T || (T <= 0 && N >= 0)) {
     *zone = 0;
-    if (f) for (int k = 0; k < dim; k++) f[k] = 0;
+    if (f) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) f[k] = 0;
+    }
   } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
     *zone = 1;
-    const int diag[4] = {0, 4, 7, 9};
-    for (int k = 0; k < dim; k++) {
-      real Dk = w->eD[r0 + k];
-      cost += (real)0.5 * Dk * x[k] * x[k];
-      if (f) f[k] = -Dk * x[k];
-      if (Hc) Hc[diag[k]] = Dk;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const int dg = k == 0 ? 0 : (k == 1 ? 4 : (k == 2 ? 7 : 9));
+      if (k < dim) {
+        real Dk = w->eD[r0 + k];
+        cost += (real)0.5 * Dk * x[k] * x[k];
+        if (f) f[k] = -Dk * x[k];
+        if (Hc) Hc[dg] = Dk;
+      } else if (f) f[k] = 0;
     }
   } else {
     *zone = 2;
@@ -608,17 +661,25 @@ DEV real mw_cone(const WarpScratch* w, const Contact* con, const real* x, real* 
     real NmT = N - mu * T;
     cost = (real)0.5 * Dm * NmT * NmT;
     real g[4] = {mu, 0, 0, 0};
-    for (int k = 1; k < dim; k++) g[k] = -mu * fr[k] * u[k] / T;
-    if (f) for (int k = 0; k < dim; k++) f[k] = -Dm * NmT * g[k];
+#pragma unroll
+    for (int k = 1; k < 4; k++) if (k < dim) g[k] = -mu * fr[k] * u[k] / T;
+    if (f) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) f[k] = k < dim ? -Dm * NmT * g[k] : (real)0;
+    }
     if (Hc) {
       real s = -Dm * NmT * mu, iT = 1 / T, iT3 = iT * iT * iT;
-      int idx = 0;
-      for (int a = 0; a < 4; a++) for (int b = a; b < 4; b++, idx++) {
-        if (a >= dim || b >= dim) continue;
-        real hv = Dm * g[a] * g[b];
-        if (a >= 1) { real t2 = -(fr[a] * u[a]) * (fr[b] * u[b]) * iT3; if (a == b) t2 += fr[a] * fr[a] * iT; hv += s * t2; }
-        Hc[idx] = hv;
-      }
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int b = a; b < 4; b++) {
+          const int idx = a == 0 ? b : (a == 1 ? 3 + b : (a == 2 ? 5 + b : 9));   // packed upper-triangular index of (a, b)
+          if (a < dim && b < dim) {
+            real hv = Dm * g[a] * g[b];
+            if (a >= 1) { real t2 = -(fr[a] * u[a]) * (fr[b] * u[b]) * iT3; if (a == b) t2 += fr[a] * fr[a] * iT; hv += s * t2; }
+            Hc[idx] = hv;
+          }
+        }
     }
   }
   return cost;
@@ -631,9 +692,12 @@ DEV real mw_constraint_eval(WarpScratch* w, int lane, bool want_hess) {
     Contact* con = &w->con[ci];
     if (con->row < 0) continue;
     real x[4] = {0, 0, 0, 0}, f[4]; int zone;
-    for (int k = 0; k < con->dim; k++) x[k] = w->eJar[con->row + k];
+    const int cdim = con->dim, crow = con->row;
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (k < cdim) x[k] = w->eJar[crow + k];
     cost += mw_cone(w, con, x, f, want_hess ? con->H : nullptr, &zone);
-    for (int k = 0; k < con->dim; k++) w->eF[con->row + k] = f[k];
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (k < cdim) w->eF[crow + k] = f[k];
     con->hzone = zone; con->fn = f[0];
   }
   return warp_sum(cost);
@@ -648,18 +712,22 @@ DEV void mw_linesearch_eval(const WarpScratch* w, int lane, real alpha, real* c,
     const Contact* con = &w->con[ci];
     if (con->row < 0) continue;
     const int r0 = con->row, dim = con->dim; const real mu = con->mu;
-    real fr[4] = {0, con->fr1, con->fr1, con->fr3};
-    real x0 = w->eJar[r0] + alpha * w->eJv[r0];
-    real N = x0 * mu, Np = w->eJv[r0] * mu, T2 = 0, xv = 0, vv = 0;
-    for (int k = 1; k < dim; k++) {
-      real fk = fr[k], jv = w->eJv[r0 + k], xk = w->eJar[r0 + k] + alpha * jv;
+    const real fr[4] = {0, con->fr1, con->fr1, con->fr3};
+    real jvk[4] = {0, 0, 0, 0}, xk4[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (k < dim) { jvk[k] = w->eJv[r0 + k]; xk4[k] = w->eJar[r0 + k] + alpha * jvk[k]; }
+    real N = xk4[0] * mu, Np = jvk[0] * mu, T2 = 0, xv = 0, vv = 0;
+#pragma unroll
+    for (int k = 1; k < 4; k++) if (k < dim) {
+      real fk = fr[k], jv = jvk[k], xk = xk4[k];
       T2 += fk * fk * xk * xk; xv += fk * fk * xk * jv; vv += fk * fk * jv * jv;
     }
     real T = sqrt(T2);
     if (N >= mu * T || (T <= 0 && N >= 0)) {
     } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
-      for (int k = 0; k < dim; k++) {
-        real Dk = w->eD[r0 + k], jv = w->eJv[r0 + k], xk = w->eJar[r0 + k] + alpha * jv;
+#pragma unroll
+      for (int k = 0; k < 4; k++) if (k < dim) {
+        real Dk = w->eD[r0 + k], jv = jvk[k], xk = xk4[k];
         cc += (real)0.5 * Dk * xk * xk; gg += Dk * xk * jv; h2 += Dk * jv * jv;
       }
     } else {
@@ -745,13 +813,22 @@ __device__ __noinline__ void mw_solve(const MwModel* __restrict__ m, WarpScratch
         const Contact* con = &w->con[c];
         if (con->row < 0 || con->hzone == 0) continue;
         const int r0 = con->row, dim = con->dim;
-        real Jb[4], t[4];
-        for (int k = 0; k < dim; k++) Jb[k] = J[(r0 + k) * NVP + lane];
-        // t = Hc * Jb (packed symmetric upper, row-major 4x4)
+        real Jb[4] = {0, 0, 0, 0}, t[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (k < dim) Jb[k] = J[(r0 + k) * NVP + lane];
+        // t = Hc * Jb (packed symmetric upper, row-major 4x4; entries beyond dim are zero)
         const real* Hc = con->H;
-        const int ix[4][4] = {{0, 1, 2, 3}, {1, 4, 5, 6}, {2, 5, 7, 8}, {3, 6, 8, 9}};
-        for (int i = 0; i < dim; i++) { real s = 0; for (int k = 0; k < dim; k++) s += Hc[ix[i][k]] * Jb[k]; t[i] = s; }
-        for (int a = lane; a < nv; a++) { real s = 0; for (int k = 0; k < dim; k++) s += J[(r0 + k) * NVP + a] * t[k]; w->H[a * NVP + lane] += s; }
+        const real h0 = Hc[0], h1 = Hc[1], h2 = Hc[2], h3 = Hc[3], h4 = Hc[4], h5 = Hc[5], h6 = Hc[6], h7 = Hc[7], h8 = Hc[8], h9 = Hc[9];
+        t[0] = h0 * Jb[0] + h1 * Jb[1] + h2 * Jb[2] + h3 * Jb[3];
+        t[1] = h1 * Jb[0] + h4 * Jb[1] + h5 * Jb[2] + h6 * Jb[3];
+        t[2] = h2 * Jb[0] + h5 * Jb[1] + h7 * Jb[2] + h8 * Jb[3];
+        t[3] = h3 * Jb[0] + h6 * Jb[1] + h8 * Jb[2] + h9 * Jb[3];
+        for (int a = lane; a < nv; a++) {
+          real s = 0;
+#pragma unroll
+          for (int k = 0; k < 4; k++) if (k < dim) s += J[(r0 + k) * NVP + a] * t[k];
+          w->H[a * NVP + lane] += s;
+        }
       }
     }
     SYNCW();
@@ -809,11 +886,11 @@ __device__ __noinline__ void mw_solve(const MwModel* __restrict__ m, WarpScratch
 #define PHASE_SYNC() __syncthreads()
 __device__ __noinline__ void mw_forward(const MwModel* __restrict__ m, const float* __restrict__ meshvert, WarpScratch* w, int lane) {
   const int nv = m->nv;
-  long long t0 = clock64(), t1;
+  long long t0 = mw_clock(), t1;
   PHASE_SYNC();
-  t1 = clock64(); if (lane == 0) w->prof[12] += t1 - t0; t0 = t1;
+  t1 = mw_clock(); if (lane == 0) w->prof[12] += t1 - t0; t0 = t1;
   // own work goes to prof[i]; the time spent waiting for the CTA's other warps at the phase boundary goes to prof[12]
-#define PROF_(i) { t1 = clock64(); if (lane == 0) w->prof[i] += t1 - t0; PHASE_SYNC(); t0 = clock64(); if (lane == 0) w->prof[12] += t0 - t1; }
+#define PROF_(i) { t1 = mw_clock(); if (lane == 0) w->prof[i] += t1 - t0; PHASE_SYNC(); t0 = mw_clock(); if (lane == 0) w->prof[12] += t0 - t1; }
   mw_kinematics(m, w, lane);
   LaneDof L; mw_lane_dof(m, w, lane, &L);
   mw_mass_matrix(m, w, L, lane);

@@ -41,25 +41,41 @@ struct MwTaskConst {
 enum { INFO_SUCCESS = 0, INFO_NEAR_OBJECT, INFO_GRASP_SUCCESS, INFO_GRASP_REWARD, INFO_IN_PLACE, INFO_OBJ_TO_TARGET, INFO_UNSCALED, INFO_N };
 
 // ---- reward utilities (metaworld/utils/reward_utils.py)
-DEV real tol_long_tail(real x, real lo, real hi, real margin) {
+// Where the reference raises ValueError (reward_utils.py:124-135 `tolerance`: lower > upper, margin < 0; :237-238
+// `hamacher_product`: inputs outside [0, 1]) a kernel cannot: the value is clamped AND the condition is recorded in the
+// env's fault word (MW_FAULT_* in include/metaworld_b200.h, read with mw_get_faults), so the host can raise.
+#define MW_FAULT_TOL_BOUNDS 1
+#define MW_FAULT_TOL_MARGIN 2
+#define MW_FAULT_HAMACHER 4
+#define MW_FAULT_NONFINITE 8
+DEV real tol_long_tail_f(int* fault, real x, real lo, real hi, real margin) {
+  if (lo > hi) *fault |= MW_FAULT_TOL_BOUNDS;
+  if (margin < 0) *fault |= MW_FAULT_TOL_MARGIN;
   if (lo <= x && x <= hi) return 1;
-  if (margin <= 0) return 0;          // reference: margin==0 -> 0, margin<0 raises; clamp-and-continue here
+  if (margin <= 0) return 0;
   real d = (x < lo ? lo - x : x - hi) / margin;
   real s = d * (real)3.0;             // sqrt(1/0.1 - 1) = 3
   return 1 / (s * s + 1);
 }
-DEV real tol_gaussian(real x, real lo, real hi, real margin) {
+DEV real tol_gaussian_f(int* fault, real x, real lo, real hi, real margin) {
+  if (lo > hi) *fault |= MW_FAULT_TOL_BOUNDS;
+  if (margin < 0) *fault |= MW_FAULT_TOL_MARGIN;
   if (lo <= x && x <= hi) return 1;
   if (margin <= 0) return 0;
   real d = (x < lo ? lo - x : x - hi) / margin;
   real s = d * (real)2.145966026289347;   // sqrt(-2 ln 0.1)
   return exp((real)-0.5 * s * s);
 }
-DEV real hamacher(real a, real b) {
+DEV real hamacher_f(int* fault, real a, real b) {
+  if (!(a >= 0 && a <= 1 && b >= 0 && b <= 1)) *fault |= MW_FAULT_HAMACHER;
   a = fmin(fmax(a, (real)0), (real)1); b = fmin(fmax(b, (real)0), (real)1);
   real den = a + b - a * b;
   return den > 0 ? a * b / den : (real)0;
 }
+// every caller has the task context `c` in scope
+#define tol_long_tail(...) tol_long_tail_f(&c.w->fault, __VA_ARGS__)
+#define tol_gaussian(...) tol_gaussian_f(&c.w->fault, __VA_ARGS__)
+#define hamacher(...) hamacher_f(&c.w->fault, __VA_ARGS__)
 DEV real dist3(const real* a, const real* b) { real t[3]; v3sub(t, a, b); return v3norm(t); }
 
 // scipy Rotation.from_matrix(M).as_quat(): xyzw with scipy's branch choice (no sign canonicalisation)

@@ -48,7 +48,7 @@ def _load(path):
     L.mw_create.argtypes = [C.POINTER(vp), ip, ip, vp, vp, C.POINTER(vp), vp]
     L.mw_destroy.argtypes = [vp]
     L.mw_set_envs.argtypes = [vp, ip, vp]
-    L.mw_build_snapshots.argtypes = [vp, ip, vp, vp, vp, vp]
+    L.mw_build_snapshots.argtypes = [vp, ip, vp, vp, vp, vp, vp]
     L.mw_append_snapshots.argtypes = [vp, ip, vp, vp]
     L.mw_num_snapshots.argtypes = [vp]
     L.mw_get_snapshots.argtypes = [vp, ip, ip, vp]
@@ -64,6 +64,8 @@ def _load(path):
     L.mw_get_profile.argtypes = [vp, vp]
     L.mw_rebalance.argtypes = [vp]
     L.mw_get_env_cost.argtypes = [vp, vp]
+    L.mw_evaluate.argtypes = [vp, vp, vp, ip, vp, vp]
+    L.mw_get_faults.argtypes = [vp, vp]
     L.mw_set_profiling.argtypes = [vp, ip]
     L.mw_get_env_profile.argtypes = [vp, vp]
     assert L.mw_sizeof_model() == lower.DTYPE.itemsize, "MwModel layout mismatch (rebuild the library)"
@@ -175,19 +177,27 @@ class Engine:
     def set_options(self, max_episode_steps=500, terminate_on_success=False, seed=0):
         _ck(lib().mw_set_options(self.h, int(max_episode_steps), int(bool(terminate_on_success)), int(seed) & (2**64 - 1)))
 
-    def build_snapshots(self, model_idx, rand_vec, partially_observable, precise=None):
+    def build_snapshots(self, model_idx, rand_vec, partially_observable, precise=None, rand_vec_pass1=None):
         """Episode-start snapshots for (model slot, rand_vec) pairs.  `precise` (default: on unless
-        MW_B200_SNAPSHOT_F32=1) runs the reset on the float64 build of the kernels and uploads the records."""
+        MW_B200_SNAPSHOT_F32=1) runs the reset on the float64 build of the kernels and uploads the records.
+        `rand_vec_pass1`: the vector of the first reset_model pass when it differs (unfrozen rand_vec, see the header)."""
         mi = np.ascontiguousarray(model_idx, dtype=np.int32)
-        rv = np.zeros((len(mi), 6), dtype=np.float32)
-        rand_vec = np.asarray(rand_vec, dtype=np.float64).reshape(len(mi), -1)
-        rv[:, : rand_vec.shape[1]] = rand_vec
+
+        def pack(v):
+            out = np.zeros((len(mi), 6), dtype=np.float32)
+            v = np.asarray(v, dtype=np.float64).reshape(len(mi), -1)
+            out[:, : v.shape[1]] = v
+            return out
+
+        rv = pack(rand_vec)
+        rv1 = None if rand_vec_pass1 is None else pack(rand_vec_pass1)
+        p1 = None if rv1 is None else rv1.ctypes.data
         po = np.ascontiguousarray(partially_observable, dtype=np.uint8)
         ids = np.zeros(len(mi), dtype=np.int32)
         if precise is None:
             precise = os.environ.get("MW_B200_SNAPSHOT_F32", "0") != "1" and SO_PATH != SO64_PATH
         if not precise:
-            _ck(lib().mw_build_snapshots(self.h, len(mi), mi.ctypes.data, rv.ctypes.data, po.ctypes.data, ids.ctypes.data))
+            _ck(lib().mw_build_snapshots(self.h, len(mi), mi.ctypes.data, rv.ctypes.data, p1, po.ctypes.data, ids.ctypes.data))
             return ids
         L = lib64()
         if self.h64 is None:
@@ -195,7 +205,7 @@ class Engine:
             self.h64 = C.c_void_p()
             _ck(L.mw_create(C.byref(self.h64), device, nm, models.ctypes.data, tcs.ctypes.data, ptrs, nmv.ctypes.data), L)
         first = L.mw_num_snapshots(self.h64)
-        _ck(L.mw_build_snapshots(self.h64, len(mi), mi.ctypes.data, rv.ctypes.data, po.ctypes.data, None), L)
+        _ck(L.mw_build_snapshots(self.h64, len(mi), mi.ctypes.data, rv.ctypes.data, p1, po.ctypes.data, None), L)
         rec = np.zeros(len(mi), dtype=SNAPSHOT_DTYPE)
         _ck(L.mw_get_snapshots(self.h64, first, len(mi), rec.ctypes.data), L)
         _ck(lib().mw_append_snapshots(self.h, len(mi), rec.ctypes.data, ids.ctypes.data))
@@ -227,6 +237,31 @@ class Engine:
         _ck(lib().mw_step(self.h, self._p(actions), self._p(obs), obs.stride(0), self._p(reward), self._p(terminated),
                           self._p(truncated), self._p(info), info.stride(0), self._p(final_obs), self._p(final_info),
                           self._p(next_snapshot), self._stream()))
+
+    def evaluate(self, actions, obs, out):
+        """evaluate_state for every env's current state: out [n, 8] = info[7], reward (mw_evaluate)."""
+        _ck(lib().mw_evaluate(self.h, self._p(actions), self._p(obs), obs.stride(0), self._p(out), self._stream()))
+
+    FAULTS = {1: "tolerance: lower bound > upper bound (the reference raises ValueError, reward_utils.py:124)",
+              2: "tolerance: margin < 0 (the reference raises ValueError, reward_utils.py:134)",
+              4: "hamacher_product: input outside [0, 1] (the reference raises ValueError, reward_utils.py:237)",
+              8: "non-finite observation or reward"}
+
+    def faults(self):
+        """Per-env MW_FAULT_* bits since the last call (cleared)."""
+        out = np.zeros(self.n_envs, dtype=np.int32)
+        self.torch.cuda.synchronize(self.device)
+        _ck(lib().mw_get_faults(self.h, out.ctypes.data))
+        return out
+
+    def raise_on_faults(self):
+        """Raises the reference's exception type for the first env that hit one of its error conditions."""
+        f = self.faults()
+        bad = np.nonzero(f)[0]
+        if len(bad):
+            e = int(bad[0])
+            msgs = [m for b, m in self.FAULTS.items() if f[e] & b]
+            raise ValueError(f"env {e}: " + "; ".join(msgs) + f" ({len(bad)} env(s) flagged)")
 
     def get_state(self):
         out = np.zeros(self.n_envs, dtype=ENVSTATE_DTYPE)

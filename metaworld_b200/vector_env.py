@@ -107,7 +107,7 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
                  env_ids=None, max_episode_steps=None, terminate_on_success=False, task_select="random",
                  reward_function_version="v2", device=0, engine=None, recurrent_info_in_obs=False,
                  normalize_reward_in_recurrent_info=True, reward_normalization_method=None, reward_alpha=0.001,
-                 normalize_observations=False, checkpoint_env_ids=None, **unused):
+                 normalize_observations=False, checkpoint_env_ids=None, type_seeds=None, **unused):
         if reward_function_version != "v2":
             raise NotImplementedError("only the default v2 rewards are implemented on the device")
         if normalize_observations:
@@ -143,7 +143,8 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
         self.sub = []
         for e in range(num_envs):
             t_i, rep = e % n_types, e // n_types
-            s = None if seed is None else seed + rep
+            # every env type shares `seed` (metaworld/__init__.py:497); the custom-mt entry point gives type i seed + i (:762)
+            s = (None if seed is None else seed + rep) if type_seeds is None else (None if type_seeds[t_i] is None else type_seeds[t_i] + rep)
             eid = reference_env_id(env_names[t_i], ck_ids[t_i]) if env_names[t_i] in TASKS else f"{env_names[t_i]}_{ck_ids[t_i]}"
             if rep:       # replicas are an extension (the reference has one sub-env per id): keep their ids distinct
                 eid += f".r{rep}"
@@ -549,12 +550,17 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
 
 def make_mt_envs(name, seed=None, num_tasks=None, num_envs=None, **kwargs):
     """``make_mt_envs`` (metaworld/__init__.py:460-513) -> MetaWorldVecEnv.  ``vector_strategy`` is accepted
-    and ignored (there is one strategy: the GPU)."""
+    and ignored (there is one strategy: the GPU).  For a task name the reference returns ONE wrapped env, not a vector
+    (:470-478): pass ``single=True`` (what ``gym.make("Meta-World/MT1", ...)`` does) to get that object."""
     from . import benchmarks as B
+
+    if kwargs.pop("single", False):
+        from .single_env import MetaWorldSingleEnv
+        return MetaWorldSingleEnv(make_mt_envs(name, seed=seed, num_tasks=num_tasks, num_envs=1, **kwargs))
 
     kwargs.pop("vector_strategy", None); kwargs.pop("autoreset_mode", None)
     bench = B.make_benchmark(name, seed, kwargs.pop("num_goals", B.N_GOALS))
-    names = bench.train_classes
+    names = list(bench.train_classes)
     default = {"MT10": 10, "MT25": 25, "MT50": 50}.get(name, 1)
     tasks = [[t for t in bench.train_tasks if t.env_name == n] for n in names]
     if name in TASKS:       # MT1: _init_each_env is called without env_id (metaworld/__init__.py:471-477)
@@ -569,7 +575,7 @@ def make_ml_envs(name, seed=None, meta_batch_size=20, total_tasks_per_cls=None, 
     kwargs.pop("vector_strategy", None); kwargs.pop("autoreset_mode", None)
     ng = kwargs.pop("num_goals", B.N_GOALS)
     bench = B.ML1(name, seed, ng) if name in TASKS else B.make_benchmark(name, seed, ng)
-    classes = bench.train_classes if split == "train" else bench.test_classes
+    classes = list(bench.train_classes if split == "train" else bench.test_classes)
     all_tasks = bench.train_tasks if split == "train" else bench.test_tasks
     assert meta_batch_size % len(classes) == 0, "meta_batch_size must be divisible by envs_per_task"
     per = meta_batch_size // len(classes)
@@ -582,4 +588,41 @@ def make_ml_envs(name, seed=None, meta_batch_size=20, total_tasks_per_cls=None, 
             names.append(n); tasks.append(ts[i::per])
     kwargs.setdefault("task_select", "pseudorandom")
     kwargs.setdefault("checkpoint_env_ids", [None] * len(names))     # _init_each_env gets no env_id here (:548-560)
+    return MetaWorldVecEnv(names, tasks, num_envs=num_envs, seed=seed, **kwargs)
+
+
+def make_custom_mt_envs(envs_list, seed=None, use_one_hot=False, num_envs=None, **kwargs):
+    """``Meta-World/custom-mt-envs`` (metaworld/__init__.py:741-783): sub-env i is ``make_mt_envs(envs_list[i],
+    num_tasks=len(envs_list), env_id=i, seed=seed + i)``, i.e. an MT1 benchmark of its own with its own seed."""
+    from . import benchmarks as B
+
+    kwargs.pop("vector_strategy", None); kwargs.pop("autoreset_mode", None)
+    ng = kwargs.pop("num_goals", B.N_GOALS)
+    seeds = [None if not seed else seed + i for i in range(len(envs_list))]
+    tasks = [B.MT1(n, sd, ng).train_tasks for n, sd in zip(envs_list, seeds)]
+    return MetaWorldVecEnv(list(envs_list), tasks, num_envs=num_envs, seed=seed, use_one_hot=use_one_hot, num_tasks=len(envs_list),
+                           type_seeds=seeds, **kwargs)
+
+
+def make_custom_ml_envs(train_envs, test_envs, seed=None, meta_batch_size=20, total_tasks_per_cls=None, split="train", num_envs=None, **kwargs):
+    """``Meta-World/custom-ml-envs`` (metaworld/__init__.py:370-395,785-820): ``CustomML`` + ``_make_ml_envs_inner``."""
+    from . import benchmarks as B
+
+    if set(train_envs) & set(test_envs):
+        raise ValueError("The test tasks cannot contain any of the train tasks.")
+    kwargs.pop("vector_strategy", None); kwargs.pop("autoreset_mode", None)
+    bench = B.Benchmark(train_envs, test_envs, True, seed, n_goals=kwargs.pop("num_goals", B.N_GOALS))
+    classes = list(bench.train_classes if split == "train" else bench.test_classes)
+    all_tasks = bench.train_tasks if split == "train" else bench.test_tasks
+    assert meta_batch_size % len(classes) == 0, "meta_batch_size must be divisible by envs_per_task"
+    per = meta_batch_size // len(classes)
+    names, tasks = [], []
+    for n in classes:
+        ts = [t for t in all_tasks if t.env_name == n]
+        if total_tasks_per_cls is not None:
+            ts = ts[:total_tasks_per_cls]
+        for i in range(per):
+            names.append(n); tasks.append(ts[i::per])
+    # _make_ml_envs_inner is reached without the pseudorandom partial here: _init_each_env's default task_select="random"
+    kwargs.setdefault("checkpoint_env_ids", [None] * len(names))
     return MetaWorldVecEnv(names, tasks, num_envs=num_envs, seed=seed, **kwargs)

@@ -428,6 +428,7 @@ static void support_local(const Shape* s, const double* dl, double* out) {
 }
 static double core_radius(const Shape* s) { return (s->type == G_SPHERE || s->type == G_CAPSULE) ? s->size[0] : 0.0; }
 static void support(const Shape* A, const Shape* B, const double* dir, SV* o) {
+  FL(60 + 6 * ((A->type == G_MESH ? A->nvert : 4) + (B->type == G_MESH ? B->nvert : 4)));
   double dl[3], l[3], nd[3] = {-dir[0], -dir[1], -dir[2]};
   mat_tmulvec(dl, A->mat, dir); support_local(A, dl, l); mat_mulvec(o->a, A->mat, l); v3add(o->a, o->a, A->pos);
   mat_tmulvec(dl, B->mat, nd); support_local(B, dl, l); mat_mulvec(o->b, B->mat, l); v3add(o->b, o->b, B->pos);
@@ -767,6 +768,7 @@ static int convex_convex(const Shape* A, const Shape* B, double margin, RawCon* 
     for (int i = 0; i < n; i++) { double t[3]; v3sub(t, s[i].v, w.v); if (v3dot(t, t) < 1e-24) dup = 1; }
     if (dup) break;
     s[n++] = w;
+    FL(150);
     if (closest_simplex(s, &n, v)) { enclosed = 1; break; }
   }
   double wa[3], wb[3];
@@ -852,6 +854,7 @@ void om_collide(const OModel* m, OData* d) {
     double margin = fmax(m->geom_margin[g1], m->geom_margin[g2]);
     double gap = fmax(m->geom_gap[g1], m->geom_gap[g2]);
     Shape a, b; get_shape(m, d, g1, &a); get_shape(m, d, g2, &b);
+    FL(12);
     /* bounding-sphere cull (a plane has no bound) */
     if (a.type == G_PLANE) {
       double n[3], t[3]; mat_col(n, a.mat, 2); v3sub(t, b.pos, a.pos);
@@ -861,6 +864,7 @@ void om_collide(const OModel* m, OData* d) {
       double bound = m->geom_rbound[g1] + m->geom_rbound[g2] + margin;
       if (v3dot(t, t) > bound * bound) continue;
     }
+    FL(a.type == G_BOX && b.type == G_BOX ? 900 : 120);      /* analytic narrowphase (box-box SAT + clipping is the large one); GJK/EPA add their own below */
     int n = narrowphase(&a, &b, margin, raw);
     for (int k = 0; k < n && d->ncon < OM_MAXCON; k++) {
       OContact* c = d->contact + d->ncon++;

@@ -55,6 +55,10 @@ struct OData {
   OContact contact[OM_MAXCON];
 };
 
+/* algorithmic flop counter of the physics passes (mul, add, div, sqrt = 1 each; counted per loop nest with its trip counts).
+ * Thread-local accumulator, folded into OData.flops by om_forward / om_step; read through om_data_flops(). */
+extern __thread long om_flops_acc;
+#define FL(n) (om_flops_acc += (long)(n))
 void om_collide(const OModel* m, OData* d);
 void om_jac(const OModel* m, const OData* d, double* jacp, double* jacr, const double* point, int body);
 int om_chol(double* L, const double* A, int n);

@@ -183,6 +183,7 @@ int om_data_nefc(const OData* d) { return d->nefc; }
 const OContact* om_data_contacts(const OData* d) { return d->contact; }
 int om_data_solver_iter(const OData* d) { return d->solver_iter; }
 long om_data_flops(const OData* d) { return d->flops; }
+__thread long om_flops_acc = 0;
 
 /* mj_resetData [3P]: qpos <- qpos0, mocap <- model body pose, everything else zero.
    Run-time edits of model.body_pos / site_pos / eq_data are NOT undone. */
@@ -272,6 +273,7 @@ static void kinematics(const OModel* m, OData* d) {
     quat_mul(qi, quat, m->body_iquat + 4 * b);
     quat2mat(d->ximat + 9 * b, qi);
   }
+  FL(m->nbody * 190 + (m->ngeom + m->nsite) * 75);   /* per body: 2 quat_mul (28) + 3 quat2mat (27) + 3 mat_mulvec (15) + normalise; per geom/site: 15 + 3 + 28 + 27 */
   for (int g = 0; g < m->ngeom; g++) {
     int b = m->geom_bodyid[g]; double t[3], q[4];
     mat_mulvec(t, d->xmat + 9 * b, m->geom_pos + 3 * g);
@@ -336,6 +338,7 @@ static void mass_matrix(const OModel* m, OData* d) {
     for (int i = 0; i < 3; i++)
       for (int j = 0; j < 3; j++)
         Iw[3 * i + j] = R[3 * i] * in[0] * R[3 * j] + R[3 * i + 1] * in[1] * R[3 * j + 1] + R[3 * i + 2] * in[2] * R[3 * j + 2];
+    FL(nc * 12 + 81 + nc * (15 + nc * 13));   /* jacobian columns, R diag R^T, nc x nc accumulation */
     for (int a = 0; a < nc; a++) {
       int da = chain[a];
       double Ija[3];
@@ -353,6 +356,7 @@ static void mass_matrix(const OModel* m, OData* d) {
 
 /* dense Cholesky A = L L^T (lower), returns 0 on success */
 int om_chol(double* L, const double* A, int n) {
+  FL((long)n * n * n / 3 + 2 * n * n);
   memcpy(L, A, sizeof(double) * (size_t)(n * n));
   for (int j = 0; j < n; j++) {
     double s = L[j * n + j];
@@ -369,6 +373,7 @@ int om_chol(double* L, const double* A, int n) {
   return 0;
 }
 void om_chol_solve(const double* L, double* x, const double* b, int n) {
+  FL(2 * n * n + 2 * n);
   for (int i = 0; i < n; i++) {
     double s = b[i];
     for (int k = 0; k < i; k++) s -= L[i * n + k] * x[k];
@@ -407,6 +412,7 @@ static void rne_bias(const OModel* m, OData* d) {
   double* cfrc = (double*)calloc((size_t)(6 * nb), sizeof(double));
   double* Sdot = (double*)calloc((size_t)(6 * (nv > 0 ? nv : 1)), sizeof(double));
   cacc[3] = -m->gravity[0]; cacc[4] = -m->gravity[1]; cacc[5] = -m->gravity[2];
+  FL((long)(nb - 1) * 260 + (long)nv * 70);       /* per body: velocity/acceleration propagation, I a + v x* I v, force accumulation; per dof: S, Sdot, projection */
   for (int b = 1; b < nb; b++) {
     int p = m->body_parentid[b];
     double v[6], a[6];
@@ -587,6 +593,7 @@ static void make_constraints(const OModel* m, OData* d) {
     int b1 = m->geom_bodyid[con->geom1], b2 = m->geom_bodyid[con->geom2];
     om_jac(m, d, jp1, jr1, con->pos, b1);
     om_jac(m, d, jp2, jr2, con->pos, b2);
+    FL(2 * nv * 12 + nv * (6 + con->dim * 6) + con->dim * (2 * nv + 40));   /* two point Jacobians, frame projection, row velocity + impedance */
     double tran = m->body_invweight0[2 * b1] + m->body_invweight0[2 * b2];
     double rot = m->body_invweight0[2 * b1 + 1] + m->body_invweight0[2 * b2 + 1];
     int r0 = d->nefc;
@@ -631,6 +638,7 @@ typedef struct {
 static double constraint_eval(const OModel* m, const OData* d, const double* jar, double* f, double* H) {
   int nv = m->nv;
   double cost = 0;
+  FL(d->nefc * 12 + (H ? (long)d->nefc * nv * nv * 2 : 0));     /* cone evaluation per row; J^T Hc J accumulation when the Hessian is requested */
   for (int i = 0; i < d->nefc; i++) {
     int type = d->efc_type[i];
     double D = d->efc_D[i];
@@ -716,6 +724,7 @@ static double constraint_eval(const OModel* m, const OData* d, const double* jar
 static void linesearch_eval(const OModel* m, const OData* d, const double* jar, const double* jv, double alpha,
                             double* cost, double* d1, double* d2) {
   double c = 0, g = 0, h = 0;
+  FL(d->nefc * 14);
   (void)m;
   for (int i = 0; i < d->nefc; i++) {
     int type = d->efc_type[i];
@@ -751,6 +760,7 @@ static void linesearch_eval(const OModel* m, const OData* d, const double* jar, 
 }
 
 static void mat_vec(double* y, const double* A, const double* x, int n) {
+  FL(2 * n * n);
   for (int i = 0; i < n; i++) { double s = 0; for (int j = 0; j < n; j++) s += A[i * n + j] * x[j]; y[i] = s; }
 }
 
@@ -783,7 +793,9 @@ static void solve_constraints(const OModel* m, OData* d) {
   }
   double cost = best;
   int iter = 0;
+  FL(3L * 2 * ne * nv + 6 * nv);            /* J a for both warm-start candidates and the selected one */
   for (; iter < m->iterations; iter++) {
+    FL(2L * 2 * ne * nv + 12 * nv + 2 * ne);   /* gradient J^T f, J search, updates */
     memcpy(H, d->qM, sizeof(double) * (size_t)(nv * nv));
     constraint_eval(m, d, jar, f, H);
     double gn = 0;
@@ -832,6 +844,7 @@ static void solve_constraints(const OModel* m, OData* d) {
   }
   constraint_eval(m, d, jar, f, NULL);
   d->solver_iter = iter;
+  FL(2L * ne * nv);
   memcpy(d->qacc, qacc, sizeof(double) * (size_t)nv);
   for (int k = 0; k < nv; k++) {
     double s = 0; for (int i = 0; i < ne; i++) s += d->efc_J[(size_t)i * nv + k] * f[i];
@@ -844,6 +857,7 @@ static void solve_constraints(const OModel* m, OData* d) {
 /* ------------------------------------------------------------------ pipeline */
 void om_forward(const OModel* m, OData* d) {
   int nv = m->nv;
+  om_flops_acc = 0;
   kinematics(m, d);
   mass_matrix(m, d);
   om_chol(d->qL, d->qM, nv);
@@ -860,6 +874,8 @@ void om_forward(const OModel* m, OData* d) {
   } else {
     solve_constraints(m, d);
   }
+  FL(6 * 2 * nv + 6 * 60 + 8 * nv);          /* weld rows (6 x nv Jacobian, impedance), passive + actuation + qfrc_smooth */
+  d->flops += om_flops_acc; om_flops_acc = 0;
 }
 
 /* semi-implicit Euler with joint damping treated implicitly  [3P mj_Euler] */
@@ -881,6 +897,8 @@ static void euler(const OModel* m, OData* d) {
     }
   }
   memcpy(d->qacc_warmstart, d->qacc, sizeof(double) * (size_t)nv);
+  FL(6 * nv + m->njnt * 4);
+  d->flops += om_flops_acc; om_flops_acc = 0;
 }
 
 void om_step(const OModel* m, OData* d, int nstep) {

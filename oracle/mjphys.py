@@ -55,6 +55,8 @@ def lib():
         L.om_data_ncon.argtypes = [C.c_void_p]
         L.om_data_nefc.argtypes = [C.c_void_p]
         L.om_data_solver_iter.argtypes = [C.c_void_p]
+        L.om_data_flops.argtypes = [C.c_void_p]
+        L.om_data_flops.restype = C.c_long
         L.om_data_contacts.argtypes = [C.c_void_p]
         L.om_data_contacts.restype = C.POINTER(_OContact)
         _LIB = L
@@ -220,6 +222,11 @@ class OData:
     @property
     def nefc(self):
         return lib().om_data_nefc(self.ptr)
+
+    @property
+    def flops(self):
+        """Floating-point operations of the physics passes run on this data so far (counted in mjphys.c)."""
+        return int(lib().om_data_flops(self.ptr))
 
     @property
     def solver_iter(self):

@@ -27,8 +27,8 @@ static void load(DShape* s, int type, const double* pos, const double* mat, cons
   for (int i = 0; i < nvert; i++) g_pack[slot][i] = float4{vert3[3 * i], vert3[3 * i + 1], vert3[3 * i + 2], 0.f};
   const float4* vert = g_pack[slot].data();
   s->type = type;
-  for (int i = 0; i < 3; i++) { s->pos[i] = pos[i]; s->size[i] = (float)size[i]; }   // sizes are float32 in MwModel
-  for (int i = 0; i < 9; i++) s->mat[i] = mat[i];
+  s->pos = pos; s->mat = mat;                                        // DShape points at the pose (the kernel: shared memory)
+  for (int i = 0; i < 3; i++) s->size[i] = (float)size[i];           // sizes are float32 in MwModel
   s->vert = vert; s->nvert = nvert;
 }
 

@@ -17,10 +17,10 @@ class OracleEngine:
         self.snaps = []           # (slot, rand_vec, partially_observable)
         self.max_steps, self.tos = 500, False
 
-    def build_snapshots(self, mi, rvs, po):
+    def build_snapshots(self, mi, rvs, po, precise=None, rand_vec_pass1=None):
         first = len(self.snaps)
-        for m, rv, p in zip(mi, rvs, po):
-            self.snaps.append((int(m), np.asarray(rv, dtype=np.float64), bool(p)))
+        for k, (m, rv, p) in enumerate(zip(mi, rvs, po)):
+            self.snaps.append((int(m), np.asarray(rv, dtype=np.float64), bool(p), None if rand_vec_pass1 is None else np.asarray(rand_vec_pass1[k], dtype=np.float64)))
         return np.arange(first, len(self.snaps), dtype=np.int32)
 
     def set_envs(self, env_model):
@@ -38,12 +38,17 @@ class OracleEngine:
         raise NotImplementedError("the device sampler has no CPU stand-in")
 
     def _start(self, e, sid):
-        slot, rv, po = self.snaps[sid]
+        slot, rv, po, rv1 = self.snaps[sid]
         assert slot == self.env_model[e]
         env = self.envs[e]
         lo, _ = env.random_reset_space()
         env.set_task_vec(rv[: len(lo)], po)
+        if rv1 is not None:          # unfrozen rand_vec: pass 1 of reset() used another draw
+            seq = [rv1[: len(lo)], rv[: len(lo)]]
+            env._get_state_rand_vec = lambda: seq.pop(0) if len(seq) > 1 else seq[0]
         o, _ = env.reset()
+        if rv1 is not None:
+            del env._get_state_rand_vec
         self.snap[e], self.plen[e], self.ret[e] = sid, 0, 0.0
         return o
 
@@ -71,12 +76,20 @@ class OracleEngine:
                 o = self._start(e, int(next_snapshot[e]))
             obs[e, :39] = torch.from_numpy(o.astype(np.float32))
 
+    def evaluate(self, actions, obs, out):
+        for e, env in enumerate(self.envs):
+            r, inf = env.evaluate_state(obs[e, :39].numpy().astype(np.float64), actions[e].numpy())
+            out[e, :7] = torch.tensor([float(inf[k]) for k in INFO_KEYS]); out[e, 7] = float(r)
+
     def get_state(self):
         st = np.zeros(self.n_envs, dtype=ENVSTATE_DTYPE)
         for e, env in enumerate(self.envs):
             st[e]["qpos"][: len(env.data.qpos)] = env.data.qpos
             st[e]["qvel"][: len(env.data.qvel)] = env.data.qvel
             st[e]["snapshot"], st[e]["path_len"], st[e]["ep_return"] = self.snap[e], self.plen[e], self.ret[e]
+            st[e]["target"] = np.asarray(env._target_pos, dtype=np.float32)
+            if env.obj_init_pos is not None:
+                st[e]["obj_init"] = np.asarray(env.obj_init_pos, dtype=np.float32)[:3]
         return st
 
     def set_state(self, st):

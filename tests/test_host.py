@@ -204,8 +204,12 @@ def test_bench_helpers():
     spec.loader.exec_module(bench)
     n = bench.usable_cores()
     assert 1 <= n <= (os.cpu_count() or 1)
-    names, total = bench.implemented_tasks("MT50")
-    assert len(names) == total == 50
+    names, total, kind = bench.benchmark_names("MT50")
+    assert len(names) == total == 50 and kind == "mt"
+    assert bench.benchmark_names("ML45-train")[0][0] == "assembly-v3" and len(bench.benchmark_names("ML45-test")[0]) == 5
+    assert bench.METRIC == __import__("json").load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
+    v, sample, flops = bench.cpu_baseline(["reach-v3"], 1, 5)
+    assert v > 0 and flops > 1e5          # oracle flop counter (oracle/mjphys.c FL): ~1.6 MFLOP per reach env step
     b = bench.algorithmic_bytes(["reach-v3"])
     assert b == 4 * (2 * 16 + 4 * 15 + 120)          # nq 16, nv 15 -> 848 B per env step
     assert abs(bench.algorithmic_bytes(names) - 792.32) < 0.5

@@ -139,3 +139,75 @@ def test_mt1_single_task_vector_and_explicit_resets(gym):
         o1, _ = renv.reset(); o2, _ = ours.reset()
         assert np.abs(o1 - o2[0]).max() < 2e-6
         assert np.array_equal(renv.unwrapped._last_rand_vec, ours.get_attr("_last_rand_vec")[0])
+
+
+def test_bare_single_env_surface_matches_reference_class(gym):
+    """`mt1.train_classes[name]()` + set_task / reset / step / evaluate_state and the attributes the reference's own tests
+    read (tests/integration/test_new_api.py:18-45, tests/metaworld/envs/mujoco/sawyer_xyz/test_sawyer_xyz_env.py)."""
+    import metaworld
+    from metaworld_b200 import benchmarks as B
+    from metaworld_b200.single_env import SawyerXYZEnvB200
+    from oracle_engine import OracleEngine
+    metaworld._N_GOALS = 3
+    name = "push-v3"
+    rb = metaworld.MT1(name, seed=5)
+    ob = B.MT1(name, seed=5, n_goals=3)
+    assert list(rb.train_classes) == list(ob.train_classes) and repr(ob.train_classes[name]) == repr(rb.train_classes[name])
+    renv = rb.train_classes[name]()
+    oenv = SawyerXYZEnvB200(name, engine=OracleEngine([name]))
+    assert oenv.task_name == renv.task_name and oenv.max_path_length == renv.max_path_length == 500
+    assert oenv._partially_observable and renv._partially_observable
+    with pytest.raises(RuntimeError):
+        oenv.step(np.zeros(4, np.float32))
+    with pytest.raises(RuntimeError):
+        renv.step(np.zeros(4, np.float32))
+    for rt, ot in zip(rb.train_tasks[:2], ob.train_tasks[:2]):
+        renv.set_task(rt); oenv.set_task(ot)
+        assert renv._partially_observable == oenv._partially_observable == False
+        assert np.array_equal(renv.sawyer_observation_space.low, oenv.observation_space.low) and np.array_equal(renv.sawyer_observation_space.high, oenv.observation_space.high)
+        o1, i1 = renv.reset(); o2, i2 = oenv.reset()
+        assert o1.dtype == o2.dtype == np.float64 and np.abs(o1 - o2).max() < 2e-6 and i1 == i2 == {}
+        assert np.array_equal(renv._last_rand_vec, oenv._last_rand_vec)
+        assert np.abs(renv._target_pos - oenv._target_pos).max() < 1e-6 and np.abs(renv.obj_init_pos - oenv.obj_init_pos).max() < 1e-6
+        rng = np.random.default_rng(1)
+        for t in range(6):
+            a = rng.uniform(-1, 1, 4).astype(np.float32)
+            x1 = renv.step(a); x2 = oenv.step(a)
+            assert np.abs(x1[0] - x2[0]).max() < 2e-6 and abs(x1[1] - x2[1]) < 1e-5 and x1[2] == x2[2] is False and x1[3] == x2[3]
+            assert set(x1[4]) == set(x2[4]) and all(abs(float(x1[4][k]) - x2[4][k]) < 1e-5 for k in KEYS)
+            assert renv.curr_path_length == oenv.curr_path_length == t + 1
+        r1, f1 = renv.evaluate_state(x1[0], a); r2, f2 = oenv.evaluate_state(x2[0], a)
+        assert abs(r1 - r2) < 1e-5 and all(abs(float(f1[k]) - f2[k]) < 1e-5 for k in KEYS)
+    with pytest.raises(AssertionError):
+        oenv.step(np.zeros(3, np.float32))
+
+
+def test_goal_hidden_and_observable_envs_draw_the_reference_goal(gym):
+    import gymnasium
+    from metaworld_b200.single_env import make_goal_env
+    from oracle_engine import OracleEngine
+    for observable, rid in ((False, "Meta-World/goal_hidden"), (True, "Meta-World/goal_observable")):
+        renv = gymnasium.make(rid, env_name="drawer-open-v3", seed=11)
+        oenv = make_goal_env("drawer-open-v3", seed=11, observable=observable, engine=OracleEngine(["drawer-open-v3"]))
+        assert np.array_equal(renv._last_rand_vec, oenv._last_rand_vec) and renv._partially_observable == oenv._partially_observable == (not observable)
+        a = np.array([0.3, -0.2, 0.1, 0.5], np.float32)
+        x1 = renv.step(a); x2 = oenv.step(a)
+        assert np.abs(x1[0] - x2[0]).max() < 2e-6 and (not x1[0][36:].any()) == (not observable)
+
+
+def test_custom_mt_and_ml_entry_points_match_reference(gym):
+    import metaworld
+    from metaworld_b200 import vector_env as V
+    from oracle_engine import OracleEngine
+    metaworld._N_GOALS = 3
+    envs = ["reach-v3", "door-open-v3", "button-press-v3"]
+    kw = dict(seed=9, use_one_hot=True, max_episode_steps=7)
+    ref = gym.make_vec("Meta-World/custom-mt-envs", vector_strategy="sync", envs_list=envs, **kw)
+    ours = V.make_custom_mt_envs(envs, engine=OracleEngine(envs), num_goals=3, **kw)
+    assert _compare_rollout(ref, ours, 16, seed=4) >= 6
+    tr, te = ["reach-v3", "push-v3"], ["door-open-v3"]
+    kw = dict(seed=2, meta_batch_size=4, max_episode_steps=6)
+    metaworld._N_GOALS = 4
+    ref = gym.make_vec("Meta-World/custom-ml-envs", vector_strategy="sync", train_envs=tr, test_envs=te, **kw)
+    ours = V.make_custom_ml_envs(tr, te, engine=OracleEngine(tr), num_goals=4, **kw)
+    assert _compare_rollout(ref, ours, 14, seed=8) >= 8
