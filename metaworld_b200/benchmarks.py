@@ -162,6 +162,10 @@ class Task:
         (metaworld/__init__.py:171); where that package is not importable the class is read back as its dotted name."""
         import io
 
+        cached = self.__dict__.get("_unpacked")
+        if cached is not None:
+            return cached
+
         class _U(pickle.Unpickler):
             def find_class(self, module, name):
                 if (module, name) == ("importlib", "import_module"):
@@ -171,7 +175,8 @@ class Task:
                 except Exception:
                     return f"{module}.{name}"
 
-        return _U(io.BytesIO(self.data)).load()
+        self.__dict__["_unpacked"] = d = _U(io.BytesIO(self.data)).load()     # cached: the hot autoreset path asks per episode
+        return d
 
 
 def draw_rand_vec(spec, rs: np.random.RandomState):

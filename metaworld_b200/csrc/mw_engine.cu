@@ -81,7 +81,7 @@ DEV void stage_model(BlockShared* bs, const unsigned char* src, unsigned bytes, 
 // wires a warp into its CTA's convex-pair queue (mw_physics.cuh: CtaShare); visible to the other warps after the first PHASE_SYNC
 DEV void join_cta(BlockShared* bs, WarpShared* wsa, WarpScratch* w, int warp, int live_warps) {
   if (threadIdx.x == 0) { bs->cs.q_head = 0; bs->cs.nwarp = live_warps; bs->cs.peer_stride = (int)sizeof(WarpShared); bs->cs.peer0 = (unsigned char*)wsa; }
-  if ((threadIdx.x & 31) == 0) { w->cta = &bs->cs; w->warp_in_cta = warp; w->ncand = 0; }
+  if ((threadIdx.x & 31) == 0) { w->cta = &bs->cs; w->warp_in_cta = warp; w->ncand = 0; w->prof_on = 0; }
   __syncwarp();
 }
 __device__ void eng_forward(const TaskCtx& c, int lane) { mw_forward(c.m, c.meshvert, c.w, lane); }
@@ -156,8 +156,9 @@ k_step(EngineDev e, const int* __restrict__ block_order, const int* __restrict__
   const MwModel* m = (const MwModel*)bs->model;
   load_env(ws, e.state + env, lane);
   if (lane < 16) w->prof[lane] = 0;
-  if (lane == 0) w->fault = 0;
-  const long long t_begin = mw_clock();
+  if (lane == 0) { w->fault = 0; w->prof_on = e.prof != nullptr; }
+  SYNCW();
+  const long long t_begin = MW_CLK(w);
   real act[4];
   for (int i = 0; i < 4; i++) act[i] = fmin(fmax((real)actions[4 * env + i], (real)-1), (real)1);
   TaskCtx c; c.m = m; c.tc = &bs->tc; c.w = w; c.s = &ws->es; c.action = act; c.meshvert = e.meshverts[mi];
@@ -165,16 +166,21 @@ k_step(EngineDev e, const int* __restrict__ block_order, const int* __restrict__
   if (lane < 3) w->mocap_pos[lane] = fmin(fmax(w->mocap_pos[lane] + act[lane] * (real)0.01, (real)bs->tc.mocap_lo[lane]), (real)bs->tc.mocap_hi[lane]);
   if (lane == 0) { w->ctrl[0] = (real)actions[4 * env + 3]; w->ctrl[1] = -(real)actions[4 * env + 3]; }
   SYNCW();
-  int iters = 0, dropped = 0, ncon_max = 0, nefc_max = 0;
+  int iters = 0, dropped = 0, ncon_max = 0, nefc_max = 0, solver_work = 0;
   for (int s = 0; s < 5; s++) {
     mw_forward(m, c.meshvert, w, lane);
     iters += w->solver_iter; dropped += w->ncon_dropped; ncon_max = max(ncon_max, w->ncon); nefc_max = max(nefc_max, w->nefc);
+    solver_work += (w->solver_iter + 1) * (w->nefc + 4 * w->ncon + 24);
     mw_euler(m, w, lane);
   }
-  mw_forward(m, c.meshvert, w, lane);
-  iters += w->solver_iter; dropped += w->ncon_dropped; ncon_max = max(ncon_max, w->ncon); nefc_max = max(nefc_max, w->nefc);
+  // mj_forward (sawyer_xyz_env.py:620): full pass only where the reward reads contact forces (same task for the whole CTA)
+  if (task_needs_contact_forces(bs->tc.task_id)) {
+    mw_forward(m, c.meshvert, w, lane);
+    iters += w->solver_iter; dropped += w->ncon_dropped; ncon_max = max(ncon_max, w->ncon); nefc_max = max(nefc_max, w->nefc);
+    solver_work += (w->solver_iter + 1) * (w->nefc + 4 * w->ncon + 24);
+  } else mw_forward_kinematics_only(m, w, lane);
   bool done = false;
-  const long long t_phys = mw_clock();
+  const long long t_phys = MW_CLK(w);
   if (lane == 0) {
     ws->es.path_len += 1.f;
     task_live_update(c);
@@ -193,14 +199,14 @@ k_step(EngineDev e, const int* __restrict__ block_order, const int* __restrict__
     ws->info[7] = (term || trunc) ? 1.f : 0.f;
     { bool fin = isfinite((float)rew); for (int i = 0; i < 39; i++) fin = fin && isfinite(ws->obs[i]); if (!fin) w->fault |= MW_FAULT_NONFINITE; }
     e.diag[3 * env] += dropped; e.diag[3 * env + 1] += iters; e.diag[3 * env + 2] |= w->fault;
-    w->prof[7] = mw_clock() - t_phys; w->prof[8] = mw_clock() - t_begin;
+    w->prof[7] = MW_CLK(w) - t_phys; w->prof[8] = MW_CLK(w) - t_begin;
     // launch-order key: the cycles this env spent in its constraint solver + constraint assembly.  The whole-step time
     // is the same for all warps of a CTA (they wait for each other at every phase boundary) and would keep light envs
     // glued to the heavy one they were once grouped with; the collision phase is shared across the CTA (CtaShare); the
     // other phases cost the same for every env of a model.  What is left to group by is the solver.
     const long long own = w->prof[8] - w->prof[12];
-    const long long key = w->prof[5] + w->prof[3];
-    e.env_cost[env] = (unsigned)(key > 0xFFFFFFFFll ? 0xFFFFFFFFll : key);
+    // (a work estimate from counters rather than the cycle clock: Newton iterations weighted by the rows they touch)
+    e.env_cost[env] = (unsigned)solver_work;
     w->prof[6] = own - w->prof[7] - (w->prof[0] + w->prof[1] + w->prof[3] + w->prof[4] + w->prof[5]);   // euler + glue
   }
   SYNCW();
@@ -372,7 +378,7 @@ k_evaluate(EngineDev e, const int* __restrict__ block_model, const int* __restri
   const MwModel* m = (const MwModel*)bs->model;
   load_env(ws, e.state + env, lane);
   if (lane < 16) w->prof[lane] = 0;
-  if (lane == 0) { w->fault = 0; w->ctrl[0] = actions[4 * env + 3]; w->ctrl[1] = -actions[4 * env + 3]; }
+  if (lane == 0) { w->fault = 0; w->prof_on = 0; w->ctrl[0] = actions[4 * env + 3]; w->ctrl[1] = -actions[4 * env + 3]; }
   SYNCW();
   mw_forward(m, e.meshverts[mi], w, lane);
   if (lane == 0) {

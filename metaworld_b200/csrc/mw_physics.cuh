@@ -58,9 +58,11 @@ struct WarpScratch {
   real eD[MW_MAXEFC], eAref[MW_MAXEFC], eJar[MW_MAXEFC], eJv[MW_MAXEFC], eF[MW_MAXEFC], eHd[MW_MAXSCALAR];
   Contact con[MW_MAXCON];
   unsigned short cand[MW_MAXCAND];   // this env's general convex candidate pairs of the current pass (pair indices)
+  unsigned char achunk[MW_MAXCON];   // 32-pair chunk each analytic contact came from (contact order, see mw_collide)
   CtaShare* cta; int warp_in_cta, ncand, pad_;
   int ncon, nefc, nscalar, nweld, solver_iter, ncon_dropped;
   int fault;                // MW_FAULT_* bits raised by the task code during this step (lane 0)
+  int prof_on;              // phase timers enabled (mw_set_profiling)
   long long prof[16];       // cycle / event counters of this step (mw_get_profile order; [12] = cycles spent waiting in PHASE_SYNC; lane 0 only)
 };
 
@@ -68,6 +70,9 @@ struct WarpScratch {
 // cycle counter that the compiler may not move across barriers / memory operations (plain clock64() was hoisted above
 // __syncthreads(), which booked every barrier wait on the phase that follows it)
 DEV long long mw_clock() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) :: "memory"); return t; }
+// Reading the clock is not free (ncu: 5.7 % of all stall samples sat on the ~80 reads per env step), so the phase timers
+// only run while profiling is switched on (mw_set_profiling); MW_CLK(w) is 0 otherwise.
+#define MW_CLK(w) ((w)->prof_on ? mw_clock() : 0ll)
 #define QSET(w, i, v) { (w)->qposd[i] = (double)(v); (w)->qpos[i] = (real)(w)->qposd[i]; }   /* write a generalized position */
 
 // ------------------------------------------------------------------ kinematics  [MuJoCo mj_kinematics]
@@ -208,21 +213,33 @@ __device__ __noinline__ void mw_mass_matrix(const MwModel* __restrict__ m, WarpS
 }
 
 // in-place dense Cholesky of the lower triangle of A (stride NVP); lane i owns row i.  returns min pivot
+// Right-looking with the lane's row held in registers (fully unrolled to MW_MAXDOF, guarded by nv): column j is scaled,
+// broadcast by shuffles and subtracted from the trailing columns.  Every element still receives its updates in increasing
+// column order, so the factor is bit-identical to the left-looking dot-product form this replaces -- at ~40 % of its
+// instruction count (the factorisation runs ~20 times per env step and was 10 % of all issued instructions).
 DEV real mw_chol(real* A, int nv, int lane) {
+  real a[MW_MAXDOF];
+#pragma unroll
+  for (int k = 0; k < MW_MAXDOF; k++) a[k] = (lane < nv && k <= lane) ? A[lane * NVP + k] : (real)0;
   real minpiv = (real)1e30;
-  for (int j = 0; j < nv; j++) {
-    real s = 0;
-    if (lane >= j && lane < nv) {
-      s = A[lane * NVP + j];
-      for (int k = 0; k < j; k++) s -= A[lane * NVP + k] * A[j * NVP + k];
+#pragma unroll
+  for (int j = 0; j < MW_MAXDOF; j++) {
+    if (j < nv) {
+      real piv = bcast(a[j], j);
+      minpiv = fmin(minpiv, piv);
+      piv = sqrt(fmax(piv, (real)1e-30));
+      const real lij = lane == j ? piv : a[j] / piv;        // L[lane][j] (meaningful for lane >= j)
+      a[j] = lij;
+#pragma unroll
+      for (int k = j + 1; k < MW_MAXDOF; k++) {
+        const real lkj = bcast(lij, k);                      // L[k][j]
+        if (k <= lane) a[k] -= lij * lkj;
+      }
     }
-    real piv = bcast(s, j);
-    minpiv = fmin(minpiv, piv);
-    piv = sqrt(fmax(piv, (real)1e-30));
-    if (lane == j) A[j * NVP + j] = piv;
-    else if (lane > j && lane < nv) A[lane * NVP + j] = s / piv;
-    SYNCW();
   }
+#pragma unroll
+  for (int k = 0; k < MW_MAXDOF; k++) if (lane < nv && k <= lane) A[lane * NVP + k] = a[k];
+  SYNCW();
   return minpiv;
 }
 // solve L L^T x = b ; lane i holds b_i / returns x_i
@@ -349,6 +366,7 @@ DEV void mw_store_contact(const MwModel* m, WarpScratch* w, int slot, const RawC
   c->g1 = m->pair_g1[pair]; c->g2 = m->pair_g2[pair];
   c->prm = (short)prm; c->dim = (unsigned char)P[2]; c->fr1 = P[3]; c->fr3 = P[4]; c->mu = P[3];
   c->row = -1; c->fn = 0; c->hzone = 0;
+  w->achunk[slot] = (unsigned char)(pair >> 5);
 }
 
 __device__ __noinline__ void mw_collide(const MwModel* __restrict__ m, const float* __restrict__ meshvert, WarpScratch* w, int lane) {
@@ -465,13 +483,38 @@ __device__ __noinline__ void mw_collide(const MwModel* __restrict__ m, const flo
         v3sub(t, sp, a.pos);
         r1.dist = v3dot(t, n); v3copy(r1.normal, n); v3addscl(r1.pos, sp, n, -(creal)0.5 * r1.dist);
         c1 = r1.dist <= mg;
-      } else { long long tc = mw_clock(); c1 = convex_pair(a, b, mg, &r1, esm, epa, lane, w->prof); if (lane == 0) { w->prof[2] += mw_clock() - tc; w->prof[9] += 1; } }
+      } else { long long tc = MW_CLK(w); c1 = convex_pair(a, b, mg, &r1, esm, epa, lane, w->prof); if (lane == 0) { w->prof[2] += MW_CLK(w) - tc; w->prof[9] += 1; } }
       if (lane == 0) { ores[k].hit = c1; if (c1) ores[k].r = r1; }
     }
   }
   __syncthreads();                       // all results are in their owners' slots
-  for (int k = 0; k < ncand; k++) {      // in pair order: the contact list is a pure function of the state
-    if (cres[k].hit) { if (ncon < MW_MAXCON && lane == 0) mw_store_contact(m, w, ncon, cres[k].r, w->cand[k]); ncon++; }
+  // Merge the convex hits into the contact list.  Order (a pure function of the state, identical to the order the pairs
+  // were visited in when every warp ran its own convex pairs inline): 32-pair chunk by chunk, within a chunk the analytic
+  // contacts first, then the convex ones in pair order.  Walk from the back so nothing is overwritten before it is moved.
+  {
+    int nhit = 0;
+    for (int k = 0; k < ncand; k++) nhit += cres[k].hit != 0;
+    const int nA = ncon < MW_MAXCON ? ncon : MW_MAXCON;      // analytic contacts actually stored
+    int j = nA + nhit - 1, ai = nA - 1, hk = ncand - 1;
+    SYNCW();
+    while (nhit > 0 && j >= 0) {
+      while (hk >= 0 && !cres[hk].hit) hk--;
+      const bool take_hit = hk >= 0 && (ai < 0 || (int)w->achunk[ai] <= (int)(w->cand[hk] >> 5));
+      if (take_hit) {
+        if (j < MW_MAXCON && lane == 0) mw_store_contact(m, w, j, cres[hk].r, w->cand[hk]);
+        hk--; nhit--;
+      } else {
+        if (j < MW_MAXCON && j != ai) {
+          const unsigned* src = (const unsigned*)&w->con[ai]; unsigned* dst = (unsigned*)&w->con[j];
+          for (int q = lane; q < (int)(sizeof(Contact) / 4); q += 32) dst[q] = src[q];
+          if (lane == 0) w->achunk[j] = w->achunk[ai];
+        }
+        ai--;
+      }
+      j--;
+      SYNCW();
+    }
+    for (int k = 0; k < ncand; k++) ncon += cres[k].hit != 0;
   }
   SYNCW();
   if (lane == 0) { w->ncon = ncon < MW_MAXCON ? ncon : MW_MAXCON; w->ncon_dropped = (ncon > MW_MAXCON ? ncon - MW_MAXCON : 0) + nover; }
@@ -769,6 +812,7 @@ __device__ __noinline__ void mw_solve(const MwModel* __restrict__ m, WarpScratch
   const real a0 = lane < nv ? w->qacc_smooth[lane] : (real)0;
   // ---- warm start selection  [mj_warmstart]
   real qacc = 0, Ma = 0, cost = 0;
+  bool warm_won = true;
   for (int pass = 0; pass < 2; pass++) {
     real a = lane < nv ? (pass == 0 ? w->warm[lane] : a0) : (real)0;
     real Maa = mw_matvec(w->M, w, a, nv, lane);
@@ -781,15 +825,16 @@ __device__ __noinline__ void mw_solve(const MwModel* __restrict__ m, WarpScratch
     real gauss = warp_sum((real)0.5 * (a - a0) * (Maa - qfs));
     real c = gauss + mw_constraint_eval(w, lane, false);
     SYNCW();
-    if (pass == 0 || c < cost) { cost = c; qacc = a; Ma = Maa; }
+    if (pass == 0 || c < cost) { cost = c; qacc = a; Ma = Maa; warm_won = pass == 0; }
   }
-  // recompute jar for the selected start (cheap, avoids branching on which pass won)
-  if (lane < nv) w->vTmp[lane] = qacc;
-  SYNCW();
-  mw_J_times(w, J, w->eJar, nefc, nv, lane);
-  SYNCW();
-  for (int r = lane; r < nefc; r += 32) w->eJar[r] -= w->eAref[r];
-  SYNCW();
+  if (warm_won) {     // eJar currently holds J a0 - aref (the second candidate): rebuild it for the warm start that won
+    if (lane < nv) w->vTmp[lane] = qacc;
+    SYNCW();
+    mw_J_times(w, J, w->eJar, nefc, nv, lane);
+    SYNCW();
+    for (int r = lane; r < nefc; r += 32) w->eJar[r] -= w->eAref[r];
+    SYNCW();
+  }
   int iter = 0;
   for (; iter < max_iter; iter++) {
     // forces + Hessian blocks at the current point
@@ -813,6 +858,10 @@ __device__ __noinline__ void mw_solve(const MwModel* __restrict__ m, WarpScratch
         const Contact* con = &w->con[c];
         if (con->row < 0 || con->hzone == 0) continue;
         const int r0 = con->row, dim = con->dim;
+        // dofs that can move either body: every other column of these rows is exactly zero, so skipping them adds nothing
+        const int cl1 = m->geom_link[con->g1], cl2 = m->geom_link[con->g2];
+        const unsigned cmask = (cl1 < 0 ? 0u : m->link_dofmask[cl1]) | (cl2 < 0 ? 0u : m->link_dofmask[cl2]);
+        if (!((cmask >> lane) & 1u)) continue;
         real Jb[4] = {0, 0, 0, 0}, t[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) if (k < dim) Jb[k] = J[(r0 + k) * NVP + lane];
@@ -823,7 +872,8 @@ __device__ __noinline__ void mw_solve(const MwModel* __restrict__ m, WarpScratch
         t[1] = h1 * Jb[0] + h4 * Jb[1] + h5 * Jb[2] + h6 * Jb[3];
         t[2] = h2 * Jb[0] + h5 * Jb[1] + h7 * Jb[2] + h8 * Jb[3];
         t[3] = h3 * Jb[0] + h6 * Jb[1] + h8 * Jb[2] + h9 * Jb[3];
-        for (int a = lane; a < nv; a++) {
+        for (unsigned rem = cmask >> lane << lane; rem; rem &= rem - 1) {
+          const int a = __ffs(rem) - 1;
           real s = 0;
 #pragma unroll
           for (int k = 0; k < 4; k++) if (k < dim) s += J[(r0 + k) * NVP + a] * t[k];
@@ -869,8 +919,7 @@ __device__ __noinline__ void mw_solve(const MwModel* __restrict__ m, WarpScratch
     cost = newcost;
     if (improvement < tol) { iter++; break; }
   }
-  mw_constraint_eval(w, lane, false);
-  SYNCW();
+  // (eF / fn are current: every exit from the loop follows an evaluation at the final point)
   real fc = 0;
   if (lane < nv) { for (int r = 0; r < nefc; r++) fc += J[r * NVP + lane] * w->eF[r]; w->qacc[lane] = qacc; w->qfrc_con[lane] = fc; }
   if (lane == 0) w->solver_iter = iter;
@@ -884,21 +933,27 @@ __device__ __noinline__ void mw_solve(const MwModel* __restrict__ m, WarpScratch
 // the same number of forward passes, so a CTA barrier at every phase boundary is legal; it keeps the CTA's warps inside the
 // same code region and lets them share the fetched lines.  (Warps that have exited are not counted by the barrier.)
 #define PHASE_SYNC() __syncthreads()
+// which of the six phase boundaries of a forward pass carry a CTA barrier (bit i = boundary i: 0 entry, 1 after kinematics +
+// inertia, 2 after collision, 3 after constraint rows, 4 after bias forces, 5 after the solver); tuned by measurement
+#ifndef MW_SYNC_MASK
+#define MW_SYNC_MASK 0x3f
+#endif
+#define PHASE_SYNC_AT(i) do { if (MW_SYNC_MASK & (1 << (i))) __syncthreads(); } while (0)
 __device__ __noinline__ void mw_forward(const MwModel* __restrict__ m, const float* __restrict__ meshvert, WarpScratch* w, int lane) {
   const int nv = m->nv;
-  long long t0 = mw_clock(), t1;
-  PHASE_SYNC();
-  t1 = mw_clock(); if (lane == 0) w->prof[12] += t1 - t0; t0 = t1;
+  long long t0 = MW_CLK(w), t1;
+  PHASE_SYNC_AT(0);
+  t1 = MW_CLK(w); if (lane == 0) w->prof[12] += t1 - t0; t0 = t1;
   // own work goes to prof[i]; the time spent waiting for the CTA's other warps at the phase boundary goes to prof[12]
-#define PROF_(i) { t1 = mw_clock(); if (lane == 0) w->prof[i] += t1 - t0; PHASE_SYNC(); t0 = mw_clock(); if (lane == 0) w->prof[12] += t0 - t1; }
+#define PROF_(i, b) { t1 = MW_CLK(w); if (lane == 0) w->prof[i] += t1 - t0; PHASE_SYNC_AT(b); t0 = MW_CLK(w); if (lane == 0) w->prof[12] += t0 - t1; }
   mw_kinematics(m, w, lane);
   LaneDof L; mw_lane_dof(m, w, lane, &L);
   mw_mass_matrix(m, w, L, lane);
-  PROF_(0)
+  PROF_(0, 1)
   mw_collide(m, meshvert, w, lane);
-  PROF_(1)
+  PROF_(1, 2)
   mw_make_constraints(m, w, L, lane);
-  PROF_(3)
+  PROF_(3, 3)
   real bias = mw_rne_bias(m, w, L, lane);
   // passive + actuation  [mj_passive, mj_fwdActuation]
   real qfs = 0;
@@ -920,10 +975,22 @@ __device__ __noinline__ void mw_forward(const MwModel* __restrict__ m, const flo
   real as = mw_chol_solve(w->H, qfs, nv, lane);
   if (lane < nv) w->qacc_smooth[lane] = as;
   SYNCW();
-  PROF_(4)
+  PROF_(4, 4)
   mw_solve(m, w, lane, sizeof(real) == 4 ? 8 : 50);
-  PROF_(5)
+  PROF_(5, 5)
 #undef PROF_
+}
+
+// positions only: what the last mj_forward of an env step contributes when nothing reads its contacts / forces
+// (same CTA barrier as the start of mw_forward, so the warps of a CTA stay phase-aligned)
+__device__ __noinline__ void mw_forward_kinematics_only(const MwModel* __restrict__ m, WarpScratch* w, int lane) {
+  long long t0 = MW_CLK(w), t1;
+  PHASE_SYNC_AT(0);
+  t1 = MW_CLK(w); if (lane == 0) w->prof[12] += t1 - t0; t0 = t1;
+  mw_kinematics(m, w, lane);
+  t1 = MW_CLK(w); if (lane == 0) w->prof[0] += t1 - t0;
+  if (lane == 0) { w->solver_iter = 0; w->ncon_dropped = 0; }
+  SYNCW();
 }
 
 // mj_Euler: semi-implicit, joint damping implicit

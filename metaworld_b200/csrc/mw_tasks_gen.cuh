@@ -111,6 +111,19 @@ DEV void task_live_update(const TaskCtx& c) {
   }
 }
 
+// Does this task's evaluate_state read contact forces (touching_object, sawyer_xyz_env.py:392-440)?  Only then does the step
+// need the constraint solve of the final mj_forward (sawyer_xyz_env.py:620); every other task reads poses only, and
+// mj_forward does not feed qacc back into the state (qacc_warmstart is written by mj_step's integrator alone [3P]), so for
+// them the 6th pass reduces to the kinematics with bit-identical results.  Keep in sync with the cases of task_reward below.
+DEV bool task_needs_contact_forces(int task_id) {
+  switch (task_id) {
+    case T_PUSH_WALL: case T_PICK_PLACE_WALL: case T_PUSH_BACK: case T_SWEEP: case T_SWEEP_INTO: case T_HAND_INSERT: case T_PUSH:
+    case T_PICK_PLACE: case T_COFFEE_PULL: case T_COFFEE_PUSH: case T_SHELF_PLACE: case T_SOCCER: case T_STICK_PULL: case T_STICK_PUSH:
+      return true;
+    default: return false;
+  }
+}
+
 // ---------------------------------------------------------------- reward + info (v2)
 DEV void task_reward(const TaskCtx& c, const real* obs, real* reward, real* info) {
   real tcp[3]; tcp_center(c, tcp);

@@ -71,3 +71,57 @@ class StepPost:
         finished = np.where(done, self.ep_return, 0.0)
         self.ep_return[done] = 0
         return obs_out, reward_out, final_out, finished
+
+
+class StepPostTorch:
+    """The same two wrappers on CUDA tensors, for `MetaWorldVecEnv.step_torch` (so RL code that keeps everything on the GPU
+    gets the recurrent observation and the normalised reward without a host round trip).  Plain torch elementwise ops on
+    [N, ...] tensors: plumbing around the engine's outputs, not a hot path."""
+
+    def __init__(self, torch, device, num_envs, obs_dim, recurrent_info_in_obs=False, normalize_reward_in_recurrent_info=True,
+                 reward_normalization_method=None, reward_alpha=0.001):
+        self.t = torch
+        self.recurrent = bool(recurrent_info_in_obs)
+        self.norm_in_obs = bool(normalize_reward_in_recurrent_info)
+        self.exponential = reward_normalization_method == "exponential"
+        self.alpha = float(reward_alpha)
+        self.mean = torch.zeros(num_envs, device=device, dtype=torch.float64)
+        self.var = torch.ones(num_envs, device=device, dtype=torch.float64)
+        self.ep_return = torch.zeros(num_envs, device=device, dtype=torch.float64)
+        self.obs_dim = obs_dim
+        self.out = torch.zeros(num_envs, obs_dim + 6, device=device) if self.recurrent else None
+        self.final_out = torch.zeros(num_envs, obs_dim + 6, device=device) if self.recurrent else None
+
+    def load_host_state(self, post: StepPost):
+        """Continue from the numpy-path statistics (a run may mix `step` and `step_torch`)."""
+        self.mean.copy_(self.t.from_numpy(post.mean)); self.var.copy_(self.t.from_numpy(post.var)); self.ep_return.copy_(self.t.from_numpy(post.ep_return))
+
+    def on_reset(self, obs):
+        self.ep_return.zero_()
+        if not self.recurrent:
+            return obs
+        self.out.zero_(); self.out[:, : self.obs_dim] = obs
+        return self.out
+
+    def on_step(self, obs, actions, reward, terminated, truncated, final_obs):
+        """-> (obs_out, reward_out [float64], final_obs_out, episode_return_of_finished_envs)"""
+        t = self.t
+        done = (terminated | truncated).bool()
+        r64 = reward.double()
+        obs_out, final_out = obs, final_obs
+        if self.recurrent:
+            r_obs = (r64 / 10.0 if self.norm_in_obs else r64).float()
+            ext = t.cat([actions, r_obs[:, None], done[:, None].float()], dim=1)
+            self.final_out[:, : self.obs_dim] = final_obs; self.final_out[:, self.obs_dim:] = ext
+            self.out[:, : self.obs_dim] = obs; self.out[:, self.obs_dim:] = t.where(done[:, None], t.zeros_like(ext), ext)
+            obs_out, final_out = self.out, self.final_out
+        reward_out = r64
+        if self.exponential:
+            for _ in range(2):          # the reference updates the estimate twice per step (wrappers.py:250-258)
+                self.mean = (1 - self.alpha) * self.mean + self.alpha * r64
+                self.var = (1 - self.alpha) * self.var + self.alpha * (r64 - self.mean) ** 2
+            reward_out = r64 / (self.var.sqrt() + 1e-8)
+        self.ep_return += reward_out
+        finished = t.where(done, self.ep_return, t.zeros_like(self.ep_return))
+        self.ep_return = t.where(done, t.zeros_like(self.ep_return), self.ep_return)
+        return obs_out, reward_out, final_out, finished

@@ -39,8 +39,11 @@ def gather_to_rank0(local, num_envs_total: int, rank: int, world: int, group=Non
     dist.all_gather_into_tensor(out, pad, group=group)
     if rank != 0:
         return None
-    res = torch.empty((num_envs_total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    for r in range(world):
-        ids = torch.as_tensor(shard_env_ids(num_envs_total, r, world), device=local.device)
-        res[ids] = out[r * n_max: r * n_max + len(ids)]
-    return res
+    if num_envs_total == world * n_max:
+        return out                      # even shards: the gathered buffer already is the global env order (contiguous blocks)
+    # uneven shards: one index op drops the padding rows (shard r's rows sit at [r * n_max, r * n_max + len_r))
+    base, rem = divmod(num_envs_total, world)
+    g = torch.arange(num_envs_total, device=local.device)
+    r_of = torch.where(g < rem * (base + 1), g // (base + 1), rem + (g - rem * (base + 1)) // max(base, 1))
+    start = r_of * base + torch.clamp(r_of, max=rem)
+    return out.index_select(0, r_of * n_max + (g - start))

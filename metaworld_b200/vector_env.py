@@ -233,7 +233,11 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
                 self._task_of_snap[int(i)] = self._task_of_snap.pop(k)
 
     def _snap(self, task: Task) -> int:
-        return self._snap_of[self._task_key(self._slot_of_name[task.env_name], task.unpack())]
+        i = task.__dict__.get("_snap_id")
+        if i is None or task.__dict__.get("_snap_owner") is not self:
+            i = self._snap_of[self._task_key(self._slot_of_name[task.env_name], task.unpack())]
+            task.__dict__["_snap_id"], task.__dict__["_snap_owner"] = i, self
+        return i
 
     def _push_next(self):
         self.h_next.copy_(self.torch.from_numpy(self._next_ids))
@@ -305,26 +309,28 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
                 infos["_" + k] = live.copy()
         fo = ep_r = None
         if any_done:
-            self.h_final_obs.copy_(self.d_final_obs, non_blocking=True)
-            self.h_final_info.copy_(self.d_final_info, non_blocking=True)
-            if self.device.type == "cuda":
-                t.cuda.current_stream(self.device).synchronize()
-            fo = self.h_final_obs.numpy().astype(self.obs_dtype)
+            # terminal observations / infos of the finished envs only (a few rows per step in steady state)
+            idx = np.nonzero(done)[0]
+            d_idx = t.from_numpy(idx).to(self.device, non_blocking=True)
+            rows_o = self.d_final_obs.index_select(0, d_idx).cpu().numpy()
+            rows_i = self.d_final_info.index_select(0, d_idx).cpu().numpy()
+            fo = np.zeros((self.num_envs, self.obs_dim), dtype=self.obs_dtype)
+            fo[idx] = rows_o
         if self.post.active:
             obs, reward, fo, ep_r = self.post.on_step(obs, a, reward, terminated, truncated, final_obs=fo)
         if any_done:
-            fi = self.h_final_info.numpy().copy()
+            fi = np.zeros((self.num_envs, 8), dtype=np.float32)
+            fi[idx] = rows_i
             if ep_r is not None:
                 fi[:, 7] = ep_r          # RecordEpisodeStatistics sits outside the reward normalisation
             final_obs = np.full(self.num_envs, None, dtype=object)
-            idx = np.nonzero(done)[0]
             for e in idx:
                 final_obs[e] = fo[e]
             final_info = {}
             for i, k in enumerate(INFO_KEYS):
-                final_info[k] = np.where(done, fi[:, i], 0.0)
+                final_info[k] = fi[:, i].astype(np.float64)        # rows of unfinished envs are 0
                 final_info["_" + k] = done.copy()
-            final_info["episode"] = {"r": np.where(done, fi[:, 7], 0.0), "l": np.where(done, self._ep_len, 0),
+            final_info["episode"] = {"r": fi[:, 7].astype(np.float64), "l": np.where(done, self._ep_len, 0),
                                      "t": np.zeros(self.num_envs), "_r": done.copy(), "_l": done.copy(), "_t": done.copy()}
             final_info["_episode"] = done.copy()
             infos["final_obs"], infos["_final_obs"] = final_obs, done.copy()
@@ -343,8 +349,8 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
     def step_wait(self):
         return self.step(self._pending_actions)
 
-    # GPU-resident variants (no host synchronisation; task re-sampling on autoreset happens on the device).  They return the
-    # engine's raw outputs: the optional recurrent-obs / reward-normalisation post-processing (post.py) is a numpy-path feature.
+    # GPU-resident variants (no host synchronisation; task re-sampling on autoreset happens on the device).  The optional
+    # recurrent-obs / reward-normalisation wrappers are applied on the device as well (post.StepPostTorch).
     def enable_device_sampler(self):
         """Autoreset draws the next goal on the device: uniform over the env's own task list, a counter-based hash of
         (seed, env, episode) -- the distribution of RandomTaskSelectWrapper, not its PCG64 stream.  The host task mirrors
@@ -361,9 +367,18 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
         self._device_sampler = False
         self._needs_reset = True
 
+    def _post_torch(self):
+        if getattr(self, "_ptorch", None) is None:
+            from .post import StepPostTorch
+            p = self.post
+            self._ptorch = StepPostTorch(self.torch, self.device, self.num_envs, self.obs_dim, p.recurrent, p.norm_in_obs,
+                                         "exponential" if p.exponential else None, p.alpha)
+            self._ptorch.load_host_state(p)
+        return self._ptorch
+
     def reset_torch(self):
         self.reset()
-        return self.d_obs
+        return self._post_torch().on_reset(self.d_obs) if self.post.active else self.d_obs
 
     def step_torch(self, actions):
         """`actions`: float32 CUDA tensor [num_envs, 4] on this env's device.  Returns device tensors (obs [N, obs_dim],
@@ -379,6 +394,10 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
         nxt = None if self._device_sampler else self.d_next
         self.engine.step(actions, self.d_obs, self.d_reward, self.d_term, self.d_trunc, self.d_small, self.d_final_obs,
                          self.d_final_info, nxt)
+        if self.post.active:       # RNNBasedMetaRLWrapper / NormalizeRewardsExponential on the device; the terminal observation
+            obs, rew, self.d_final_obs_post, self.d_episode_return_post = self._post_torch().on_step(    # and episode returns stay available
+                self.d_obs, actions, self.d_reward, self.d_term, self.d_trunc, self.d_final_obs)
+            return obs, rew, self.d_term, self.d_trunc, self.d_info
         return self.d_obs, self.d_reward, self.d_term, self.d_trunc, self.d_info
 
     # attribute RPC used by metaworld/evaluation.py:48-169 and the reference tests
