@@ -118,7 +118,7 @@ int mw_rebalance(mw_engine*);
 /* Profiling switch (default off: the timed kernel then carries no profiling atomics).  When on, mw_step additionally sums
  * the per-phase counters below, the per-model cost used by mw_rebalance, and records per env [20] u32: the 13 counters of
  * mw_get_profile for that env's last step, [13] solver iterations, [14] / [15] largest contact / constraint-row
- * count over the 6 passes, [16] launch slot (CTA).  Stands in for nothing in the reference (it has no profiler hook on this path).  */
+ * count over the 6 passes, [16] launch slot (CTA), [17] convex candidate pairs queued.  Stands in for nothing in the reference (it has no profiler hook on this path).  */
 int mw_set_profiling(mw_engine*, int on);
 int mw_get_env_profile(mw_engine*, unsigned* out /*host [n_envs*20]*/);
 

@@ -166,18 +166,18 @@ k_step(EngineDev e, const int* __restrict__ block_order, const int* __restrict__
   if (lane < 3) w->mocap_pos[lane] = fmin(fmax(w->mocap_pos[lane] + act[lane] * (real)0.01, (real)bs->tc.mocap_lo[lane]), (real)bs->tc.mocap_hi[lane]);
   if (lane == 0) { w->ctrl[0] = (real)actions[4 * env + 3]; w->ctrl[1] = -(real)actions[4 * env + 3]; }
   SYNCW();
-  int iters = 0, dropped = 0, ncon_max = 0, nefc_max = 0, solver_work = 0;
+  int iters = 0, dropped = 0, ncon_max = 0, nefc_max = 0, solver_work = 0, cand_total = 0;
   for (int s = 0; s < 5; s++) {
     mw_forward(m, c.meshvert, w, lane);
     iters += w->solver_iter; dropped += w->ncon_dropped; ncon_max = max(ncon_max, w->ncon); nefc_max = max(nefc_max, w->nefc);
-    solver_work += (w->solver_iter + 1) * (w->nefc + 4 * w->ncon + 24);
+    solver_work += (w->solver_iter + 1) * (w->nefc + 4 * w->ncon + 24); cand_total += w->ncand;
     mw_euler(m, w, lane);
   }
   // mj_forward (sawyer_xyz_env.py:620): full pass only where the reward reads contact forces (same task for the whole CTA)
   if (task_needs_contact_forces(bs->tc.task_id)) {
     mw_forward(m, c.meshvert, w, lane);
     iters += w->solver_iter; dropped += w->ncon_dropped; ncon_max = max(ncon_max, w->ncon); nefc_max = max(nefc_max, w->nefc);
-    solver_work += (w->solver_iter + 1) * (w->nefc + 4 * w->ncon + 24);
+    solver_work += (w->solver_iter + 1) * (w->nefc + 4 * w->ncon + 24); cand_total += w->ncand;
   } else mw_forward_kinematics_only(m, w, lane);
   bool done = false;
   const long long t_phys = MW_CLK(w);
@@ -219,6 +219,7 @@ k_step(EngineDev e, const int* __restrict__ block_order, const int* __restrict__
       if (lane == 14) e.env_prof[MW_ENVPROF_W * env + 14] = (unsigned)ncon_max;
       if (lane == 15) e.env_prof[MW_ENVPROF_W * env + 15] = (unsigned)nefc_max;
       if (lane == 16) e.env_prof[MW_ENVPROF_W * env + 16] = (unsigned)blockIdx.x;
+      if (lane == 17) e.env_prof[MW_ENVPROF_W * env + 17] = (unsigned)cand_total;      // convex candidate pairs this env queued
     }
   }
   done = ws->info[7] != 0.f;
@@ -425,6 +426,9 @@ __global__ void k_order_envs(const int* __restrict__ model_first, const int* __r
     keys[i] = key;
   }
   bitonic_sort_u64(keys, P);
+  // (tried: dealing the heaviest envs one per CTA so that their convex pairs are shared by lighter CTA-mates - the slowest
+  //  CTA got 25 % faster, but every CTA of the model then waits for a heavy solver: 3.63 instead of 3.40 ms per step.  Plain
+  //  cost order, i.e. CTAs of similar envs, is what is measured fastest.)
   for (int i = threadIdx.x; i < n; i += blockDim.x) perm[first + i] = (int)(keys[i] & 0xFFFFFFFFull);
 }
 __global__ void k_order_blocks(int n_blocks, const int* __restrict__ block_start, const int* __restrict__ perm, const unsigned* __restrict__ env_cost, int* __restrict__ block_order) {

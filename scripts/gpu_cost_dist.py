@@ -11,14 +11,15 @@ env.reset(); env.enable_device_sampler()
 g = torch.Generator(device=env.device); g.manual_seed(1)
 for step in range(1, 401):
     a = torch.rand(N, 4, device=env.device, generator=g) * 2 - 1
+    env.engine.set_profiling(step in (5, 50, 100, 200, 300, 400))      # phase timers only on the sampled steps
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); env.step_torch(a); e1.record()
     if step in (5, 50, 100, 200, 300, 400):
         torch.cuda.synchronize()
-        c = env.engine.env_cost().astype(np.float64) / 1e6
+        P = env.engine.env_profile().astype(np.float64); c = (P[:, 8] - P[:, 12]) / 1e6      # own work (barrier waits excluded)
         em = env.engine.env_model
         q = np.quantile(c, [0.5, 0.9, 0.99, 0.999, 1.0])
-        print(f"step {step}: kernel {e0.elapsed_time(e1):.2f} ms | env cost Mcycles mean {c.mean():.2f} p50 {q[0]:.2f} p90 {q[1]:.2f} p99 {q[2]:.2f} p99.9 {q[3]:.2f} max {q[4]:.2f} | ideal {c.sum()/(148*8)/1965*1e3:.2f} ms")
+        print(f"step {step}: kernel {e0.elapsed_time(e1):.2f} ms | env cost Mcycles mean {c.mean():.2f} p50 {q[0]:.2f} p90 {q[1]:.2f} p99 {q[2]:.2f} p99.9 {q[3]:.2f} max {q[4]:.2f} | balanced {c.sum()/(148*7)/1965*1e3:.2f} ms | slowest CTA {P[:, 8].max()/1965e3:.2f} ms")
         top = np.argsort(-c)[:8]
         print("   heaviest:", [(names[em[i]], round(c[i], 1)) for i in top])
         bym = sorted(((c[em == m].mean(), names[m]) for m in range(50)), reverse=True)[:6]

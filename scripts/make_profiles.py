@@ -6,10 +6,17 @@ os.makedirs(P, exist_ok=True)
 
 def jl(path): return json.load(open(path))
 
-# 1. bench lines
-for src, dst in (("bench_mt50.json", f"{R}_bench_mt50.json"), ("bench_ref.json", f"{R}_bench_reference.json")):
+# 1. bench lines (one per BASELINE config that fits one GPU, + both arms of the headline, + the driver's 20-step window)
+for src, dst in (("bench_mt50.json", f"{R}_bench_mt50.json"), ("bench_ref.json", f"{R}_bench_reference.json"),
+                 ("bench_mt50_driver_window.json", f"{R}_bench_mt50_driver_window.json"), ("bench_mt10.json", f"{R}_bench_mt10.json"),
+                 ("bench_reach.json", f"{R}_bench_reach_v3.json"), ("bench_ml45_train.json", f"{R}_bench_ml45_train.json"),
+                 ("bench_ml45_test.json", f"{R}_bench_ml45_test.json"), ("bench_2gpu_gather.json", f"{R}_bench_2gpu_gather.json"),
+                 ("bench_2gpu.json", f"{R}_bench_2gpu.json"), ("bench_8gpu.json", f"{R}_bench_8gpu.json"), ("bench_8gpu_gather.json", f"{R}_bench_8gpu_gather.json")):
     if os.path.exists(os.path.join(G, src)):
-        d = jl(os.path.join(G, src)); json.dump(d, open(os.path.join(P, dst), "w"), indent=1)
+        try:
+            d = jl(os.path.join(G, src)); json.dump(d, open(os.path.join(P, dst), "w"), indent=1)
+        except Exception as e:
+            print("skip", src, e)
 
 # 2. launch list -> per-kernel summary (ncu --metrics gpu__time_duration.sum; cold-cache, serialised: shares only)
 rows = [r for r in csv.reader(open(os.path.join(G, "launches.csv"))) if r and r[0].isdigit()]
@@ -34,7 +41,10 @@ want = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct", "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
-        "smsp__inst_executed_pipe_fp64.sum", "smsp__inst_executed_pipe_fma.sum", "smsp__inst_executed_pipe_lsu.sum", "sm__cycles_elapsed.avg"]
+        "smsp__inst_executed_pipe_fp64.sum", "smsp__inst_executed_pipe_fma.sum", "smsp__inst_executed_pipe_lsu.sum", "sm__cycles_elapsed.avg",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum"]
+for i, hname in enumerate(h):
+    if hname.startswith("smsp__pcsamp_warps_issue_stalled_") and not hname.endswith("_not_issued"): want.append(hname)
 with open(os.path.join(P, f"{R}_k_step_ncu_summary.csv"), "w") as f:
     f.write("metric,value,unit\n")
     for w in want:
@@ -42,14 +52,16 @@ with open(os.path.join(P, f"{R}_k_step_ncu_summary.csv"), "w") as f:
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
 open("/tmp/_src.csv", "w").write(src)
 hot = subprocess.run([sys.executable, "scripts/ncu_lines.py", "/tmp/_src.csv", "30"], capture_output=True, text=True).stdout
-open(os.path.join(P, f"{R}_k_step_hotspots.txt"), "w").write("k_step, MT50 4096 envs, launch #100 of an episode (ncu --set full --import-source on; stall samples and executed warp instructions by function / line)\n" + hot)
+open(os.path.join(P, f"{R}_k_step_hotspots.txt"), "w").write("k_step, MT50 4096 envs, steady state (episode phases uniform over 0..499, scripts/gpu_ncu_target.py; ncu --set full --import-source on; stall samples and executed warp instructions by function / line)\n" + hot)
+if os.path.exists(os.path.join(G, "cost_distribution.txt")):
+    open(os.path.join(P, f"{R}_cost_distribution.txt"), "w").write(open(os.path.join(G, "cost_distribution.txt")).read())
 
 # 4. per-task table
 rows = [json.loads(l) for l in open(os.path.join(G, "task_times.jsonl"))]
 rows.sort(key=lambda r: -r["mcycles"])
 with open(os.path.join(P, f"{R}_task_times.md"), "w") as f:
     f.write("Per-task step cost: 888 envs of one task, 20 random-action steps after 3 warm-up steps (scripts/gpu_task_times.py).\n"
-            "`Mcyc` = mean warp cycles per env step (1 warp = 1 env); phases as fractions of that; events per env step.\n\n")
+            "`Mcyc` = mean OWN-WORK warp cycles per env step (1 warp = 1 env; time spent waiting for CTA-mates at phase barriers excluded); phases as fractions of that; events per env step.\n\n")
     f.write("| task | ms/step | Mcyc | collide | of which GJK/EPA | solver | convex pairs | EPA expansions | GJK iters | Newton its/pass |\n|---|---|---|---|---|---|---|---|---|---|\n")
     for r in rows:
         f.write(f"| {r['task']} | {r['ms']:.2f} | {r['mcycles']:.2f} | {r['collide']:.2f} | {r['gjk']:.2f} | {r['solver']:.2f} | {r['pairs']:.1f} | {r['epa']:.1f} | {r['gjkit']:.1f} | {r['newton']:.2f} |\n")
@@ -59,13 +71,22 @@ ol = {r[0]: r for r in csv.reader(open(os.path.join(G, "open_loop.csv")))}
 cr = {r[0]: r for r in csv.reader(open(os.path.join(G, "contact_rich.csv")))}
 xf = [l.strip() for l in open(os.path.join(G, "pytest.log")) if l.startswith("XFAIL")]
 with open(os.path.join(P, f"{R}_parity.md"), "w") as f:
-    f.write("Device (float32 step, float64 collision, float64 reset snapshots) vs oracle (float64), through the C ABI on a B200.\n"
+    f.write("Device (float32 step, float64 collision, float64 reset snapshots) vs goldens (the reference's env classes run unmodified on restated float64 physics), through the C ABI on a B200; obs, reward and all 7 info keys.\n"
             "Open loop: 60 random-action steps from reset, 3 goals, worst absolute error over the rollout.  Contact rich: single steps teacher-forced\n"
             "from the oracle's state along trajectories driven by the reference's scripted policy (238 steps per task).\n\n")
     f.write("| task | open-loop worst obs err | open-loop worst reward err | contact-rich: frac of steps within 1e-4 | median err | p90 err | worst err |\n|---|---|---|---|---|---|---|\n")
     for t in sorted(set(ol) | set(cr)):
         o = ol.get(t, ["", "", "-", "-"]); c = cr.get(t, ["", "", "-", "-", "-", "-"])
         f.write(f"| {t} | {o[2]} | {o[3]} | {c[2]} | {c[3]} | {c[4]} | {c[5]} |\n")
+    lr = {r[0]: r for r in csv.reader(open(os.path.join(G, "long_rollout.csv")))} if os.path.exists(os.path.join(G, "long_rollout.csv")) else {}
+    ps = {r[0]: r for r in csv.reader(open(os.path.join(G, "policy_success.csv")))} if os.path.exists(os.path.join(G, "policy_success.csv")) else {}
+    f.write("\nFull 500-step open-loop episodes (worst |obs, reward, info| error up to step 60 / 125 / 250 / 500) and scripted-policy action replays "
+            "(successes out of 5 goals: device / reference glue on the oracle):\n\n| task | <=60 | <=125 | <=250 | <=500 | policy replay device | reference glue |\n|---|---|---|---|---|---|---|\n")
+    for t in sorted(set(lr) | set(ps)):
+        a = lr.get(t, [t, "-", "-", "-", "-"]); b = ps.get(t, [t, "-", "-"])
+        f.write(f"| {t} | {a[1]} | {a[2]} | {a[3]} | {a[4]} | {b[1]} | {b[2]} |\n")
+    summ = [l.strip() for l in open(os.path.join(G, "pytest.log")) if " passed" in l or " failed" in l]
+    f.write("\nGPU suite of this run: " + "; ".join(summ) + "\n")
     f.write("\nxfail list of this run (pytest -rx):\n\n")
     for l in xf: f.write(f"* `{l}`\n")
 print(open(os.path.join(P, f"{R}_launches_summary.csv")).read())

@@ -377,7 +377,9 @@ def test_partially_observable_rollout_matches_golden(torch_cuda, task):
 
 # A full 500-step random-action episode against the float64 golden, open loop (no teacher forcing).  Measured on B200
 # (profiles/r02_parity.md): 49 of 50 tasks stay within 1e-5 for the whole episode; basketball starts exactly touching.
-SENSITIVE_LONG = {"basketball-v3": _TOUCH}
+_INFO_GAIN = ("observations and reward agree to 1e-5 over the whole episode; one info value (a steep shaping term of the coffee tasks' "
+              "evaluate_state) amplifies that to {} - measured, profiles/r02_parity.md")
+SENSITIVE_LONG = {"basketball-v3": _TOUCH, "coffee-pull-v3": _INFO_GAIN.format("1.7e-4"), "coffee-push-v3": _INFO_GAIN.format("9.1e-4")}
 
 
 @pytest.mark.parametrize("task", _params(SENSITIVE_LONG))

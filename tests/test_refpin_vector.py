@@ -211,3 +211,23 @@ def test_custom_mt_and_ml_entry_points_match_reference(gym):
     ref = gym.make_vec("Meta-World/custom-ml-envs", vector_strategy="sync", train_envs=tr, test_envs=te, **kw)
     ours = V.make_custom_ml_envs(tr, te, engine=OracleEngine(tr), num_goals=4, **kw)
     assert _compare_rollout(ref, ours, 14, seed=8) >= 8
+
+
+def test_every_reference_id_has_an_entry_point(gym):
+    """The ids the reference registers (metaworld/__init__.py:607-820) == the ids this package registers, and the entry
+    points take the reference's argument names."""
+    import metaworld_b200 as M
+    from oracle_engine import OracleEngine
+    ref_ids = {k.split("/", 1)[1] for k in gym.registry if k.startswith("Meta-World/")}
+    table = M.entry_points()
+    assert ref_ids == set(table), (sorted(ref_ids - set(table)), sorted(set(table) - ref_ids))
+    for k, (single, vec) in table.items():
+        spec = gym.registry["Meta-World/" + k]
+        assert (single is not None) >= (spec.entry_point is not None) and (vec is not None) >= (spec.vector_entry_point is not None), k   # (MT1 additionally has a vector form here)
+    v = table["MT10"][1](seed=1, use_one_hot=True, vector_strategy="sync", num_goals=2, engine=OracleEngine(M.MT10))
+    assert v.num_envs == 10 and v.single_observation_space.shape == (49,)
+    e = table["MT1"][0](env_name="reach-v3", seed=1, num_goals=2, engine=OracleEngine(["reach-v3"]))
+    o, _ = e.reset()
+    assert o.shape == (39,) and e.step(np.zeros(4, np.float32))[0].shape == (39,)
+    ml = table["ML10-test"][1](seed=1, meta_batch_size=5, num_goals=2, engine=OracleEngine(M.ML10["test"]))
+    assert ml.num_envs == 5 and ml.get_attr("terminate_on_success") == tuple([True] * 5)      # make_ml_envs_test (:603-605)
