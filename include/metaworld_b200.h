@@ -24,7 +24,7 @@ int mw_sizeof_taskconst(void);
 int mw_sizeof_envstate(void);   /* 512 bytes */
 int mw_sizeof_snapshot(void);   /* 768 bytes */
 const char* mw_last_error(void);
-const char* mw_build_info(void); /* "real=float maxcon=48 maxefc=216 warps_per_block=7 ..." */
+const char* mw_build_info(void); /* "real=float maxcon=80(shared 48) maxefc=344(shared 216) warps_per_block=7 ..." */
 
 /* Construction: what MujocoEnv.__init__ -> MjModel.from_xml_path does per sub-env
  * (metaworld/sawyer_xyz_env.py:53-63), for n_models distinct (model, task) slots.

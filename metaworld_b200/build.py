@@ -80,6 +80,24 @@ def _build_f64(force=False, verbose=False):
     return SO_F64
 
 
+def build_variant(path, defines=(), force=False):
+    """A build of the float32 engine with extra -D macros (test-only: e.g. MW_SMCON=6 makes almost every env take the
+    overflow path, whose results must be bit-identical to the standard build; tests/test_gpu.py)."""
+    write_header()
+    srcs = [os.path.join(CSRC, f) for f in SOURCES + HEADERS + ["mw_model.h", "mw_task_ids.h"]]
+    if not force and os.path.exists(path) and os.path.getmtime(path) >= max(os.path.getmtime(d) for d in srcs):
+        return path
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    cmd = [nvcc] + [f"-D{d}" for d in defines] + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-DMW_NO_FASTMATH",
+                                                  "-Xcompiler", "-fPIC", "-shared", "-o", path] + [os.path.join(CSRC, s) for s in SOURCES]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("nvcc failed (variant build)")
+    return path
+
+
 if __name__ == "__main__":
     if "--double" in sys.argv:
         print(build(force=True, verbose="-v" in sys.argv, real_double=True))

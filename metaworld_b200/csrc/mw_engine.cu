@@ -36,6 +36,7 @@ struct EngineDev {
   const int* goal_first; const int* goal_count;      // device sampler ranges (may be NULL)
   int* diag;                                         // [n_envs][3]: contacts dropped, solver iterations, MW_FAULT_* bits (OR)
   EpaWs* epa;                                        // GJK/EPA polytope workspace, one per launched warp (global memory)
+  WarpSpill* spill;                                  // overflow contacts / constraint rows, one block per launched warp (global memory)
   unsigned long long* prof;                          // [16] summed cycle / event counters (mw_get_profile)
   unsigned long long* model_cycles;                  // [n_models][2]: warp cycles, env steps (drives mw_rebalance)
   unsigned* env_cost;                                // [n_envs] warp cycles of each env's previous step (drives the launch order)
@@ -151,6 +152,7 @@ k_step(EngineDev e, const int* __restrict__ block_order, const int* __restrict__
   const int env = perm[block_start[blk] + warp];
   WarpShared* ws = wsa + warp;
   ws->w.epa = e.epa + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp);
+  ws->w.sp = e.spill + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp);
   WarpScratch* w = &ws->w;
   join_cta(bs, wsa, w, warp, block_count[blk]);
   const MwModel* m = (const MwModel*)bs->model;
@@ -264,6 +266,7 @@ k_snapshot(EngineDev e, const int* __restrict__ block_model, const int* __restri
   const int item = perm[block_start[blockIdx.x] + warp];
   WarpShared* ws = wsa + warp;
   ws->w.epa = e.epa + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp);
+  ws->w.sp = e.spill + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp);
   WarpScratch* w = &ws->w;
   join_cta(bs, wsa, w, warp, block_count[blockIdx.x]);
   const MwModel* m = (const MwModel*)bs->model;
@@ -335,6 +338,7 @@ k_substeps(EngineDev e, const int* __restrict__ block_model, const int* __restri
   const int env = perm[block_start[blockIdx.x] + warp];
   WarpShared* ws = wsa + warp;
   ws->w.epa = e.epa + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp);
+  ws->w.sp = e.spill + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp);
   join_cta(bs, wsa, &ws->w, warp, block_count[blockIdx.x]);
   const MwModel* m = (const MwModel*)bs->model;
   load_env(ws, e.state + env, lane);
@@ -345,7 +349,7 @@ k_substeps(EngineDev e, const int* __restrict__ block_model, const int* __restri
     mw_forward(m, e.meshverts[mi], &ws->w, lane);
     float* d = dump + (size_t)env * (MW_MAXCON * 12 + MW_MAXDOF + 4);
     for (int c = lane; c < MW_MAXCON; c += 32) {
-      const Contact* k = &ws->w.con[c];
+      const Contact* k = mw_con(&ws->w, c);
       bool ok = c < ws->w.ncon;
       d[12 * c + 0] = ok ? (float)k->dist : 0.f;
       for (int i = 0; i < 3; i++) { d[12 * c + 1 + i] = ok ? (float)k->pos[i] : 0.f; d[12 * c + 4 + i] = ok ? (float)k->frame[i] : 0.f; }
@@ -374,6 +378,7 @@ k_evaluate(EngineDev e, const int* __restrict__ block_model, const int* __restri
   const int env = perm[block_start[blockIdx.x] + warp];
   WarpShared* ws = wsa + warp;
   ws->w.epa = e.epa + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp);
+  ws->w.sp = e.spill + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp);
   WarpScratch* w = &ws->w;
   join_cta(bs, wsa, w, warp, block_count[blockIdx.x]);
   const MwModel* m = (const MwModel*)bs->model;
@@ -451,7 +456,7 @@ struct mw_engine {
   std::vector<float*> meshbufs;
   MwEnvState* d_state = nullptr; MwSnapshot* d_snaps = nullptr; int snap_cap = 0, n_snaps = 0;
   int *d_goal_first = nullptr, *d_goal_count = nullptr, *d_diag = nullptr;
-  EpaWs* d_epa = nullptr; size_t epa_cap = 0;
+  EpaWs* d_epa = nullptr; WarpSpill* d_spill = nullptr; size_t epa_cap = 0;
   unsigned long long* d_prof = nullptr; unsigned long long* d_model_cycles = nullptr; unsigned* d_env_prof = nullptr; int profiling = 0;
   unsigned* d_env_cost = nullptr; int *d_block_order = nullptr, *d_model_first = nullptr, *d_model_count = nullptr; int n_sorted_models = 0;
   std::vector<int> h_faults;                                   // fault bits already drained from d_diag by mw_get_counters
@@ -462,7 +467,7 @@ struct mw_engine {
   unsigned long long launches = 0, env_steps = 0;
   EngineDev dev() const {
     EngineDev e; e.models = d_models; e.model_stride = model_stride; e.taskconsts = d_tc; e.meshverts = d_meshptrs;
-    e.state = d_state; e.snaps = d_snaps; e.goal_first = d_goal_first; e.goal_count = d_goal_count; e.diag = d_diag; e.epa = d_epa; e.prof = profiling ? d_prof : nullptr; e.model_cycles = d_model_cycles; e.env_cost = d_env_cost; e.env_prof = profiling ? d_env_prof : nullptr;
+    e.state = d_state; e.snaps = d_snaps; e.goal_first = d_goal_first; e.goal_count = d_goal_count; e.diag = d_diag; e.epa = d_epa; e.spill = d_spill; e.prof = profiling ? d_prof : nullptr; e.model_cycles = d_model_cycles; e.env_cost = d_env_cost; e.env_prof = profiling ? d_env_prof : nullptr;
     e.n_envs = n_envs; e.max_steps = max_steps; e.terminate_on_success = terminate_on_success; e.seed = seed; return e;
   }
 };
@@ -485,8 +490,10 @@ static int ensure_epa(mw_engine* E, size_t n_blocks) {
   size_t need = n_blocks * WARPS_PER_BLOCK;
   if (need <= E->epa_cap) return 0;
   if (E->d_epa) cudaFree(E->d_epa);
-  E->d_epa = nullptr; E->epa_cap = 0;
+  if (E->d_spill) cudaFree(E->d_spill);
+  E->d_epa = nullptr; E->d_spill = nullptr; E->epa_cap = 0;
   CK(cudaMalloc((void**)&E->d_epa, sizeof(EpaWs) * need));
+  CK(cudaMalloc((void**)&E->d_spill, sizeof(WarpSpill) * need));
   E->epa_cap = need;
   return 0;
 }
@@ -525,8 +532,8 @@ int mw_sizeof_snapshot(void) { return (int)sizeof(MwSnapshot); }
 const char* mw_last_error(void) { return g_err.c_str(); }
 const char* mw_build_info(void) {
   static char buf[256];
-  snprintf(buf, sizeof(buf), "real=%s maxcon=%d maxefc=%d warps_per_block=%d smem_per_block=%zu", sizeof(real) == 4 ? "float" : "double",
-           MW_MAXCON, MW_MAXEFC, WARPS_PER_BLOCK, smem_bytes());
+  snprintf(buf, sizeof(buf), "real=%s maxcon=%d(shared %d) maxefc=%d(shared %d) warps_per_block=%d smem_per_block=%zu", sizeof(real) == 4 ? "float" : "double",
+           MW_MAXCON, MW_SMCON, MW_MAXEFC, MW_SMEFC, WARPS_PER_BLOCK, smem_bytes());
   return buf;
 }
 
@@ -578,7 +585,7 @@ void mw_destroy(mw_engine* E) {
   cudaSetDevice(E->device);
   cudaFree(E->d_models); cudaFree(E->d_tc); cudaFree(E->d_meshptrs);
   for (float* p : E->meshbufs) cudaFree(p);
-  cudaFree(E->d_state); cudaFree(E->d_snaps); cudaFree(E->d_goal_first); cudaFree(E->d_goal_count); cudaFree(E->d_diag); cudaFree(E->d_epa); cudaFree(E->d_prof); cudaFree(E->d_model_cycles); cudaFree(E->d_env_prof); cudaFree(E->d_env_cost); cudaFree(E->d_block_order); cudaFree(E->d_model_first); cudaFree(E->d_model_count);
+  cudaFree(E->d_state); cudaFree(E->d_snaps); cudaFree(E->d_goal_first); cudaFree(E->d_goal_count); cudaFree(E->d_diag); cudaFree(E->d_epa); cudaFree(E->d_spill); cudaFree(E->d_prof); cudaFree(E->d_model_cycles); cudaFree(E->d_env_prof); cudaFree(E->d_env_cost); cudaFree(E->d_block_order); cudaFree(E->d_model_first); cudaFree(E->d_model_count);
   cudaFree(E->d_block_model); cudaFree(E->d_block_start); cudaFree(E->d_block_count); cudaFree(E->d_perm);
   delete E;
 }

@@ -13,11 +13,22 @@
 #include "mw_collide.cuh"
 
 #define NVP 17               // row stride of the dense nv x nv / nefc x nv matrices (odd: conflict-free columns)
+// Capacities.  The warp's shared-memory scratch holds MW_SMCON contacts and MW_SMEFC constraint rows: enough for all but
+// ~1e-4 of env steps (p99.99 of the per-step contact maximum is 37).  An env that exceeds them in some pass - a jam: e.g. a
+// plug wedged in its socket with 6 box-box pairs x 8 points - is NOT truncated: contacts MW_SMCON.. and rows MW_SMEFC.. go to
+// a per-warp global-memory block (WarpSpill) and that pass runs the <SP = true> instantiation of the constraint code, which
+// addresses rows / contacts through a storage selector.  Same arithmetic, same order: results do not depend on where a row
+// lives (checked by building with tiny shared capacities and comparing digests, scripts/gpu_ab.py).  Only beyond MW_MAXCON /
+// MW_MAXEFC is a contact dropped, and counted.
+#ifndef MW_SMCON
+#define MW_SMCON 48
+#endif
 #ifndef MW_MAXCON
-#define MW_MAXCON 48
+#define MW_MAXCON 80
 #endif
 #define MW_MAXSCALAR 24      // weld (6) + joint-limit rows
-#define MW_MAXEFC (MW_MAXSCALAR + 4 * MW_MAXCON)   // worst case: every contact condim 4
+#define MW_SMEFC (MW_MAXSCALAR + 4 * MW_SMCON)     // every shared-memory contact can be condim 4
+#define MW_MAXEFC (MW_MAXSCALAR + 4 * MW_MAXCON)
 
 enum { JT_FREE = 0, JT_BALL, JT_SLIDE, JT_HINGE };
 
@@ -32,7 +43,7 @@ struct Contact {
 };
 
 // region U is time-shared: (a) geom world poses + EPA workspace during collision, (b) efc_J afterwards
-#define MW_UWORDS_J (MW_MAXEFC * NVP)
+#define MW_UWORDS_J (MW_SMEFC * NVP)
 #define MW_UWORDS_C (MW_MAXGEOM * 12 * 2 + (int)(sizeof(EpaSm) / 4) + 2 + MW_MAXCAND * (int)(sizeof(ConvRes) / 4))   // geom world poses (creal) + EPA scratch + convex-pair results during collision
 #define MW_UWORDS (MW_UWORDS_J > MW_UWORDS_C ? MW_UWORDS_J : MW_UWORDS_C)
 
@@ -41,6 +52,8 @@ struct Contact {
 // (and the kernel: the slowest env's collision phase was the critical path of the whole step).
 #define MW_MAXCAND 48
 struct CtaShare { int q_head, nwarp, peer_stride, pad; unsigned char* peer0; int q_cnt[16]; };
+
+struct WarpSpill;
 
 struct WarpScratch {
   real lpos[MW_MAXLINK][3], lquat[MW_MAXLINK][4], lmat[MW_MAXLINK][9];
@@ -55,8 +68,9 @@ struct WarpScratch {
   real M[MW_MAXDOF * NVP], H[MW_MAXDOF * NVP];
   alignas(16) real U[MW_UWORDS];
   EpaWs* epa;               // this warp's GJK/EPA polytope workspace (global memory, see mw_engine.cu)
-  real eD[MW_MAXEFC], eAref[MW_MAXEFC], eJar[MW_MAXEFC], eJv[MW_MAXEFC], eF[MW_MAXEFC], eHd[MW_MAXSCALAR];
-  Contact con[MW_MAXCON];
+  WarpSpill* sp;            // overflow storage for contacts >= MW_SMCON / rows >= MW_SMEFC (global memory)
+  real eD[MW_SMEFC], eAref[MW_SMEFC], eJar[MW_SMEFC], eJv[MW_SMEFC], eF[MW_SMEFC], eHd[MW_MAXSCALAR];
+  Contact con[MW_SMCON];
   unsigned short cand[MW_MAXCAND];   // this env's general convex candidate pairs of the current pass (pair indices)
   unsigned char achunk[MW_MAXCON];   // 32-pair chunk each analytic contact came from (contact order, see mw_collide)
   CtaShare* cta; int warp_in_cta, ncand, pad_;
@@ -65,6 +79,20 @@ struct WarpScratch {
   int prof_on;              // phase timers enabled (mw_set_profiling)
   long long prof[16];       // cycle / event counters of this step (mw_get_profile order; [12] = cycles spent waiting in PHASE_SYNC; lane 0 only)
 };
+
+struct WarpSpill {
+  real J[(MW_MAXEFC - MW_SMEFC) * NVP];
+  real eD[MW_MAXEFC - MW_SMEFC], eAref[MW_MAXEFC - MW_SMEFC], eJar[MW_MAXEFC - MW_SMEFC], eJv[MW_MAXEFC - MW_SMEFC], eF[MW_MAXEFC - MW_SMEFC];
+  Contact con[MW_MAXCON - MW_SMCON];
+};
+// storage selectors (used by the SP = true instantiations and by the few cold call sites that may see any contact index)
+DEV real* mw_jrow(const WarpScratch* w, int r) { return r < MW_SMEFC ? (real*)w->U + r * NVP : w->sp->J + (r - MW_SMEFC) * NVP; }
+DEV real* mw_ev(const real* sm, real* gl, int r) { return r < MW_SMEFC ? (real*)sm + r : gl + (r - MW_SMEFC); }
+DEV Contact* mw_con(const WarpScratch* w, int c) { return c < MW_SMCON ? (Contact*)&w->con[c] : &w->sp->con[c - MW_SMCON]; }
+// inside `template <bool SP>` functions: direct shared-memory addressing unless this pass overflowed
+#define JROW(r) (SP ? mw_jrow(w, (r)) : (real*)w->U + (r) * NVP)
+#define EV(name, r) (*(SP ? mw_ev(w->name, w->sp->name, (r)) : (real*)&w->name[r]))
+#define CON(c) (SP ? mw_con(w, (c)) : (Contact*)&w->con[c])
 
 #define SYNCW() __syncwarp()
 // cycle counter that the compiler may not move across barriers / memory operations (plain clock64() was hoisted above
@@ -355,7 +383,7 @@ DEV void make_frame(creal* fr) {
   v3cross(z, fr, y);
 }
 DEV void mw_store_contact(const MwModel* m, WarpScratch* w, int slot, const RawCon& rc, int pair) {
-  Contact* c = &w->con[slot];
+  Contact* c = mw_con(w, slot);
   int prm = m->pair_param[pair];
   const float* P = m->param[prm];
   c->dist = (real)rc.dist;
@@ -505,7 +533,7 @@ __device__ __noinline__ void mw_collide(const MwModel* __restrict__ m, const flo
         hk--; nhit--;
       } else {
         if (j < MW_MAXCON && j != ai) {
-          const unsigned* src = (const unsigned*)&w->con[ai]; unsigned* dst = (unsigned*)&w->con[j];
+          const unsigned* src = (const unsigned*)mw_con(w, ai); unsigned* dst = (unsigned*)mw_con(w, j);
           for (int q = lane; q < (int)(sizeof(Contact) / 4); q += 32) dst[q] = src[q];
           if (lane == 0) w->achunk[j] = w->achunk[ai];
         }
@@ -549,8 +577,7 @@ DEV RowParam mw_impedance(real pos_minus_margin, const real* solref, const real*
   return r;
 }
 
-__device__ __noinline__ void mw_make_constraints(const MwModel* __restrict__ m, WarpScratch* w, const LaneDof& L, int lane) {
-  real* J = w->U;
+template <bool SP> __device__ __noinline__ void mw_make_constraints(const MwModel* __restrict__ m, WarpScratch* w, const LaneDof& L, int lane) {
   const int nv = m->nv;
   const real h = m->timestep;
   // ---- weld rows 0..5 (mocap -> hand)
@@ -570,7 +597,7 @@ __device__ __noinline__ void mw_make_constraints(const MwModel* __restrict__ m, 
     mw_jac_col(L, m->link_dofmask[wl], lane, ph, jp, jr);
     real axq[4] = {0, -jr[0], -jr[1], -jr[2]}, a4[4], b4[4];
     quat_mul(a4, q1n, axq); quat_mul(b4, a4, q);
-    if (lane < nv) for (int k = 0; k < 3; k++) { J[k * NVP + lane] = -jp[k]; J[(3 + k) * NVP + lane] = (real)0.5 * ts * b4[1 + k]; }
+    if (lane < nv) for (int k = 0; k < 3; k++) { JROW(k)[lane] = -jp[k]; JROW(3 + k)[lane] = (real)0.5 * ts * b4[1 + k]; }
   }
   int nrow = 6;
   // ---- joint limits
@@ -584,16 +611,16 @@ __device__ __noinline__ void mw_make_constraints(const MwModel* __restrict__ m, 
   int nlim = __popc(lm);
   if (nrow + nlim > MW_MAXSCALAR) { nlim = MW_MAXSCALAR - nrow; }
   int myrank = __popc(lm & ((1u << lane) - 1));
-  for (int r = 0; r < nlim; r++) if (lane < nv) J[(nrow + r) * NVP + lane] = 0;
+  for (int r = 0; r < nlim; r++) if (lane < nv) JROW(nrow + r)[lane] = 0;
   SYNCW();
-  if ((lim_lo || lim_hi) && myrank < nlim) J[(nrow + myrank) * NVP + lane] = lim_lo ? (real)1 : (real)-1;
+  if ((lim_lo || lim_hi) && myrank < nlim) JROW(nrow + myrank)[lane] = lim_lo ? (real)1 : (real)-1;
   // per-row scalars for limit rows are filled below by the owning dof lane
   const int nscalar = nrow + nlim;
   // ---- contact rows
   int nefc = nscalar;
   const int ncon = w->ncon;
   for (int c = 0; c < ncon; c++) {
-    Contact* con = &w->con[c];
+    Contact* con = CON(c);
     if (con->dist >= (real)m->param[con->prm][1]) { if (lane == 0) con->row = -1; continue; }
     if (nefc + con->dim > MW_MAXEFC) { if (lane == 0) { con->row = -1; w->ncon_dropped++; } continue; }   // counted, reported by mw_get_counters
     int l1 = m->geom_link[con->g1], l2 = m->geom_link[con->g2];
@@ -604,8 +631,8 @@ __device__ __noinline__ void mw_make_constraints(const MwModel* __restrict__ m, 
     mw_jac_col(L, m2, lane, p, jp2, jr2);
     real dp[3], dr[3]; v3sub(dp, jp2, jp1); v3sub(dr, jr2, jr1);
     if (lane < nv) {
-      for (int k = 0; k < 3; k++) J[(nefc + k) * NVP + lane] = v3dot(con->frame + 3 * k, dp);
-      if (con->dim > 3) J[(nefc + 3) * NVP + lane] = v3dot(con->frame, dr);
+      for (int k = 0; k < 3; k++) JROW(nefc + k)[lane] = v3dot(con->frame + 3 * k, dp);
+      if (con->dim > 3) JROW(nefc + 3)[lane] = v3dot(con->frame, dr);
     }
     if (lane == 0) con->row = nefc;
     nefc += con->dim;
@@ -613,13 +640,13 @@ __device__ __noinline__ void mw_make_constraints(const MwModel* __restrict__ m, 
   SYNCW();
   // ---- per-row scalars: weld (lanes 0..5), limits (owning dof lane), contacts (lane c)
   if (lane < 6) {
-    real vel = 0; for (int k = 0; k < nv; k++) vel += J[lane * NVP + k] * w->qvel[k];
+    real vel = 0; for (int k = 0; k < nv; k++) vel += JROW(lane)[k] * w->qvel[k];
     real sr[2] = {m->weld_solref[0], m->weld_solref[1]}, si[5] = {m->weld_solimp[0], m->weld_solimp[1], m->weld_solimp[2], m->weld_solimp[3], m->weld_solimp[4]};
     RowParam rp = mw_impedance(cpos[lane], sr, si, h);
     real diag = lane < 3 ? m->weld_invw[0] : m->weld_invw[1];
     real Rr = fmax(MW_EPS, (1 - rp.imp) * diag / rp.imp);
-    w->eD[lane] = 1 / Rr;
-    w->eAref[lane] = -rp.B * vel - rp.K * rp.imp * cpos[lane];
+    EV(eD, lane) = 1 / Rr;
+    EV(eAref, lane) = -rp.B * vel - rp.K * rp.imp * cpos[lane];
   }
   if ((lim_lo || lim_hi) && myrank < nlim) {
     int r = nrow + myrank;
@@ -627,11 +654,11 @@ __device__ __noinline__ void mw_make_constraints(const MwModel* __restrict__ m, 
     real sr[2] = {(real)0.02, (real)1}, si[5] = {(real)0.9, (real)0.95, (real)0.001, (real)0.5, (real)2};
     RowParam rp = mw_impedance(ldist, sr, si, h);
     real Rr = fmax(MW_EPS, (1 - rp.imp) * m->dof_invweight[lane] / rp.imp);
-    w->eD[r] = 1 / Rr;
-    w->eAref[r] = -rp.B * vel - rp.K * rp.imp * ldist;
+    EV(eD, r) = 1 / Rr;
+    EV(eAref, r) = -rp.B * vel - rp.K * rp.imp * ldist;
   }
   for (int ci = lane; ci < ncon; ci += 32) {
-    Contact* con = &w->con[ci];
+    Contact* con = CON(ci);
     if (con->row < 0) continue;
     int r0 = con->row, dim = con->dim;
     real tran = m->geom_invw[con->g1][0] + m->geom_invw[con->g2][0];
@@ -647,9 +674,9 @@ __device__ __noinline__ void mw_make_constraints(const MwModel* __restrict__ m, 
     const real Rk[4] = {R0, R1, R1, R1 * con->fr1 * con->fr1 / (con->fr3 * con->fr3)};
 #pragma unroll
     for (int k = 0; k < 4; k++) if (k < dim) {
-      real vel = 0; for (int d = 0; d < nv; d++) vel += J[(r0 + k) * NVP + d] * w->qvel[d];
-      w->eD[r0 + k] = 1 / Rk[k];
-      w->eAref[r0 + k] = k == 0 ? (-rp.B * vel - rp.K * rp.imp * (con->dist - incl)) : (-rf.B * vel);
+      real vel = 0; for (int d = 0; d < nv; d++) vel += JROW(r0 + k)[d] * w->qvel[d];
+      EV(eD, r0 + k) = 1 / Rk[k];
+      EV(eAref, r0 + k) = k == 0 ? (-rp.B * vel - rp.K * rp.imp * (con->dist - incl)) : (-rf.B * vel);
     }
   }
   if (lane == 0) { w->nefc = nefc; w->nscalar = nscalar; w->nweld = 6; }
@@ -658,8 +685,8 @@ __device__ __noinline__ void mw_make_constraints(const MwModel* __restrict__ m, 
 
 // ------------------------------------------------------------------ constraint cost / force / Hessian blocks
 // scalar rows on lanes [0,nscalar), contacts on lanes [0,ncon) (two passes); x = jar (+ alpha*jv).
-DEV real mw_scalar_row(const WarpScratch* w, int r, real x, real* f, real* hd) {
-  real D = w->eD[r];
+template <bool SP> DEV real mw_scalar_row(const WarpScratch* w, int r, real x, real* f, real* hd) {
+  real D = EV(eD, r);
   bool active = (r < w->nweld) || x < 0;
   *f = active ? -D * x : (real)0; *hd = active ? D : (real)0;
   return active ? (real)0.5 * D * x * x : (real)0;
@@ -667,7 +694,7 @@ DEV real mw_scalar_row(const WarpScratch* w, int r, real x, real* f, real* hd) {
 // elliptic cone block; x[0..dim) ; optionally forces and packed Hessian.  All loops run to the fixed bound 4 with a
 // `k < dim` guard and are fully unrolled: the small arrays then live in registers instead of the thread's local-memory
 // stack (dynamically indexed arrays were the bulk of the kernel's 5.9 K LDL/STL instructions and of its DRAM traffic).
-DEV real mw_cone(const WarpScratch* w, const Contact* con, const real* x, real* f, real* Hc, int* zone) {
+template <bool SP> DEV real mw_cone(const WarpScratch* w, const Contact* con, const real* x, real* f, real* Hc, int* zone) {
   const int r0 = con->row, dim = con->dim;
   const real mu = con->mu;
   const real fr[4] = {0, con->fr1, con->fr1, con->fr3};
@@ -692,7 +719,7 @@ DEV real mw_cone(const WarpScratch* w, const Contact* con, const real* x, real* 
     for (int k = 0; k < 4; k++) {
       const int dg = k == 0 ? 0 : (k == 1 ? 4 : (k == 2 ? 7 : 9));
       if (k < dim) {
-        real Dk = w->eD[r0 + k];
+        real Dk = EV(eD, r0 + k);
         cost += (real)0.5 * Dk * x[k] * x[k];
         if (f) f[k] = -Dk * x[k];
         if (Hc) Hc[dg] = Dk;
@@ -700,7 +727,7 @@ DEV real mw_cone(const WarpScratch* w, const Contact* con, const real* x, real* 
     }
   } else {
     *zone = 2;
-    real Dm = w->eD[r0] / fmax(MW_EPS, mu * mu * (1 + mu * mu));
+    real Dm = EV(eD, r0) / fmax(MW_EPS, mu * mu * (1 + mu * mu));
     real NmT = N - mu * T;
     cost = (real)0.5 * Dm * NmT * NmT;
     real g[4] = {mu, 0, 0, 0};
@@ -728,37 +755,37 @@ DEV real mw_cone(const WarpScratch* w, const Contact* con, const real* x, real* 
   return cost;
 }
 // full evaluation at jar: returns total constraint cost; stores forces (eF), scalar Hessian diag (eHd) and cone Hessians
-DEV real mw_constraint_eval(WarpScratch* w, int lane, bool want_hess) {
+template <bool SP> DEV real mw_constraint_eval(WarpScratch* w, int lane, bool want_hess) {
   real cost = 0;
-  if (lane < w->nscalar) { real f, hd; cost += mw_scalar_row(w, lane, w->eJar[lane], &f, &hd); w->eF[lane] = f; w->eHd[lane] = hd; }
+  if (lane < w->nscalar) { real f, hd; cost += mw_scalar_row<SP>(w, lane, EV(eJar, lane), &f, &hd); EV(eF, lane) = f; w->eHd[lane] = hd; }
   for (int ci = lane; ci < w->ncon; ci += 32) {
-    Contact* con = &w->con[ci];
+    Contact* con = CON(ci);
     if (con->row < 0) continue;
     real x[4] = {0, 0, 0, 0}, f[4]; int zone;
     const int cdim = con->dim, crow = con->row;
 #pragma unroll
-    for (int k = 0; k < 4; k++) if (k < cdim) x[k] = w->eJar[crow + k];
-    cost += mw_cone(w, con, x, f, want_hess ? con->H : nullptr, &zone);
+    for (int k = 0; k < 4; k++) if (k < cdim) x[k] = EV(eJar, crow + k);
+    cost += mw_cone<SP>(w, con, x, f, want_hess ? con->H : nullptr, &zone);
 #pragma unroll
-    for (int k = 0; k < 4; k++) if (k < cdim) w->eF[crow + k] = f[k];
+    for (int k = 0; k < 4; k++) if (k < cdim) EV(eF, crow + k) = f[k];
     con->hzone = zone; con->fn = f[0];
   }
   return warp_sum(cost);
 }
-DEV void mw_linesearch_eval(const WarpScratch* w, int lane, real alpha, real* c, real* g, real* hh) {
+template <bool SP> DEV void mw_linesearch_eval(const WarpScratch* w, int lane, real alpha, real* c, real* g, real* hh) {
   real cc = 0, gg = 0, h2 = 0;
   if (lane < w->nscalar) {
-    real jv = w->eJv[lane], x = w->eJar[lane] + alpha * jv, D = w->eD[lane];
+    real jv = EV(eJv, lane), x = EV(eJar, lane) + alpha * jv, D = EV(eD, lane);
     if (lane < w->nweld || x < 0) { cc += (real)0.5 * D * x * x; gg += D * x * jv; h2 += D * jv * jv; }
   }
   for (int ci = lane; ci < w->ncon; ci += 32) {
-    const Contact* con = &w->con[ci];
+    const Contact* con = CON(ci);
     if (con->row < 0) continue;
     const int r0 = con->row, dim = con->dim; const real mu = con->mu;
     const real fr[4] = {0, con->fr1, con->fr1, con->fr3};
     real jvk[4] = {0, 0, 0, 0}, xk4[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int k = 0; k < 4; k++) if (k < dim) { jvk[k] = w->eJv[r0 + k]; xk4[k] = w->eJar[r0 + k] + alpha * jvk[k]; }
+    for (int k = 0; k < 4; k++) if (k < dim) { jvk[k] = EV(eJv, r0 + k); xk4[k] = EV(eJar, r0 + k) + alpha * jvk[k]; }
     real N = xk4[0] * mu, Np = jvk[0] * mu, T2 = 0, xv = 0, vv = 0;
 #pragma unroll
     for (int k = 1; k < 4; k++) if (k < dim) {
@@ -770,11 +797,11 @@ DEV void mw_linesearch_eval(const WarpScratch* w, int lane, real alpha, real* c,
     } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
 #pragma unroll
       for (int k = 0; k < 4; k++) if (k < dim) {
-        real Dk = w->eD[r0 + k], jv = jvk[k], xk = xk4[k];
+        real Dk = EV(eD, r0 + k), jv = jvk[k], xk = xk4[k];
         cc += (real)0.5 * Dk * xk * xk; gg += Dk * xk * jv; h2 += Dk * jv * jv;
       }
     } else {
-      real Dm = w->eD[r0] / fmax(MW_EPS, mu * mu * (1 + mu * mu));
+      real Dm = EV(eD, r0) / fmax(MW_EPS, mu * mu * (1 + mu * mu));
       real NmT = N - mu * T, Tp = xv / T, Tpp = vv / T - xv * xv / (T * T * T);
       real r = Np - mu * Tp;
       cc += (real)0.5 * Dm * NmT * NmT; gg += Dm * NmT * r; h2 += Dm * (r * r - NmT * mu * Tpp);
@@ -793,18 +820,17 @@ DEV real mw_matvec(const real* A, WarpScratch* w, real x, int nv, int lane) {
   return s;
 }
 // rows of J times a dof vector held in vTmp -> out[r]
-DEV void mw_J_times(const WarpScratch* w, const real* J, real* out, int nefc, int nv, int lane) {
+template <bool SP> DEV void mw_J_times(const WarpScratch* w, real* out_sm, real* out_gl, int nefc, int nv, int lane) {
   for (int r = lane; r < nefc; r += 32) {
     real s = 0;
-    for (int k = 0; k < nv; k++) s += J[r * NVP + k] * w->vTmp[k];
-    out[r] = s;
+    for (int k = 0; k < nv; k++) s += JROW(r)[k] * w->vTmp[k];
+    *(SP ? mw_ev(out_sm, out_gl, r) : out_sm + r) = s;
   }
 }
 
 // ------------------------------------------------------------------ solver  [MuJoCo mj_solNewton, primal]
 // minimise 1/2 (a-a0)^T M (a-a0) + s(J a - aref).  Newton with exact Hessian + exact 1-D line search.
-__device__ __noinline__ void mw_solve(const MwModel* __restrict__ m, WarpScratch* w, int lane, int max_iter) {
-  real* J = w->U;
+template <bool SP> __device__ __noinline__ void mw_solve(const MwModel* __restrict__ m, WarpScratch* w, int lane, int max_iter) {
   const int nv = m->nv, nefc = w->nefc;
   const real scale = m->solver_scale;
   const real tol = sizeof(real) == 4 ? (real)1e-7 : (real)1e-10;
@@ -818,31 +844,31 @@ __device__ __noinline__ void mw_solve(const MwModel* __restrict__ m, WarpScratch
     real Maa = mw_matvec(w->M, w, a, nv, lane);
     if (lane < nv) w->vTmp[lane] = a;
     SYNCW();
-    mw_J_times(w, J, w->eJar, nefc, nv, lane);
+    mw_J_times<SP>(w, w->eJar, w->sp->eJar, nefc, nv, lane);
     SYNCW();
-    for (int r = lane; r < nefc; r += 32) w->eJar[r] -= w->eAref[r];
+    for (int r = lane; r < nefc; r += 32) EV(eJar, r) -= EV(eAref, r);
     SYNCW();
     real gauss = warp_sum((real)0.5 * (a - a0) * (Maa - qfs));
-    real c = gauss + mw_constraint_eval(w, lane, false);
+    real c = gauss + mw_constraint_eval<SP>(w, lane, false);
     SYNCW();
     if (pass == 0 || c < cost) { cost = c; qacc = a; Ma = Maa; warm_won = pass == 0; }
   }
   if (warm_won) {     // eJar currently holds J a0 - aref (the second candidate): rebuild it for the warm start that won
     if (lane < nv) w->vTmp[lane] = qacc;
     SYNCW();
-    mw_J_times(w, J, w->eJar, nefc, nv, lane);
+    mw_J_times<SP>(w, w->eJar, w->sp->eJar, nefc, nv, lane);
     SYNCW();
-    for (int r = lane; r < nefc; r += 32) w->eJar[r] -= w->eAref[r];
+    for (int r = lane; r < nefc; r += 32) EV(eJar, r) -= EV(eAref, r);
     SYNCW();
   }
   int iter = 0;
   for (; iter < max_iter; iter++) {
     // forces + Hessian blocks at the current point
-    mw_constraint_eval(w, lane, true);
+    mw_constraint_eval<SP>(w, lane, true);
     SYNCW();
     // gradient
     real grad = 0;
-    if (lane < nv) { grad = Ma - qfs; for (int r = 0; r < nefc; r++) grad -= J[r * NVP + lane] * w->eF[r]; }
+    if (lane < nv) { grad = Ma - qfs; for (int r = 0; r < nefc; r++) grad -= JROW(r)[lane] * EV(eF, r); }
     real gn = sqrt(warp_sum(grad * grad));
     if (scale * gn < tol) break;
     // H = M + J^T Hblocks J : lane b owns column b, lower triangle a >= b
@@ -851,11 +877,11 @@ __device__ __noinline__ void mw_solve(const MwModel* __restrict__ m, WarpScratch
       for (int r = 0; r < w->nscalar; r++) {
         real hd = w->eHd[r];
         if (hd == 0) continue;
-        real wb = hd * J[r * NVP + lane];
-        if (wb != 0) for (int a = lane; a < nv; a++) w->H[a * NVP + lane] += J[r * NVP + a] * wb;
+        real wb = hd * JROW(r)[lane];
+        if (wb != 0) for (int a = lane; a < nv; a++) w->H[a * NVP + lane] += JROW(r)[a] * wb;
       }
       for (int c = 0; c < w->ncon; c++) {
-        const Contact* con = &w->con[c];
+        const Contact* con = CON(c);
         if (con->row < 0 || con->hzone == 0) continue;
         const int r0 = con->row, dim = con->dim;
         // dofs that can move either body: every other column of these rows is exactly zero, so skipping them adds nothing
@@ -864,7 +890,7 @@ __device__ __noinline__ void mw_solve(const MwModel* __restrict__ m, WarpScratch
         if (!((cmask >> lane) & 1u)) continue;
         real Jb[4] = {0, 0, 0, 0}, t[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) if (k < dim) Jb[k] = J[(r0 + k) * NVP + lane];
+        for (int k = 0; k < 4; k++) if (k < dim) Jb[k] = JROW(r0 + k)[lane];
         // t = Hc * Jb (packed symmetric upper, row-major 4x4; entries beyond dim are zero)
         const real* Hc = con->H;
         const real h0 = Hc[0], h1 = Hc[1], h2 = Hc[2], h3 = Hc[3], h4 = Hc[4], h5 = Hc[5], h6 = Hc[6], h7 = Hc[7], h8 = Hc[8], h9 = Hc[9];
@@ -876,7 +902,7 @@ __device__ __noinline__ void mw_solve(const MwModel* __restrict__ m, WarpScratch
           const int a = __ffs(rem) - 1;
           real s = 0;
 #pragma unroll
-          for (int k = 0; k < 4; k++) if (k < dim) s += J[(r0 + k) * NVP + a] * t[k];
+          for (int k = 0; k < 4; k++) if (k < dim) s += JROW(r0 + k)[a] * t[k];
           w->H[a * NVP + lane] += s;
         }
       }
@@ -887,19 +913,19 @@ __device__ __noinline__ void mw_solve(const MwModel* __restrict__ m, WarpScratch
     real Ms = mw_matvec(w->M, w, search, nv, lane);
     if (lane < nv) w->vTmp[lane] = search;
     SYNCW();
-    mw_J_times(w, J, w->eJv, nefc, nv, lane);
+    mw_J_times<SP>(w, w->eJv, w->sp->eJv, nefc, nv, lane);
     SYNCW();
     // exact line search (safeguarded Newton on a convex C1 function)
     real c1 = warp_sum(search * (Ma - qfs)), c2 = warp_sum(search * Ms);
     real cc, g1, g2;
-    mw_linesearch_eval(w, lane, 0, &cc, &g1, &g2);
+    mw_linesearch_eval<SP>(w, lane, 0, &cc, &g1, &g2);
     real p1 = c1 + g1, p2 = c2 + g2;
     if (!(p1 < 0)) break;
     const real p10 = p1;
     real lo = 0, hi = -1, alpha = -p1 / p2;
     const real lstol = sizeof(real) == 4 ? (real)1e-5 : (real)1e-12;
     for (int ls = 0; ls < 24; ls++) {
-      mw_linesearch_eval(w, lane, alpha, &cc, &g1, &g2);
+      mw_linesearch_eval<SP>(w, lane, alpha, &cc, &g1, &g2);
       p1 = c1 + alpha * c2 + g1; p2 = c2 + g2;
       if (fabs(p1) < lstol * fabs(p10)) break;
       if (p1 < 0) lo = alpha; else hi = alpha;
@@ -910,10 +936,10 @@ __device__ __noinline__ void mw_solve(const MwModel* __restrict__ m, WarpScratch
       alpha = an;
     }
     qacc += alpha * search; Ma += alpha * Ms;
-    for (int r = lane; r < nefc; r += 32) w->eJar[r] += alpha * w->eJv[r];
+    for (int r = lane; r < nefc; r += 32) EV(eJar, r) += alpha * EV(eJv, r);
     SYNCW();
     real gauss = warp_sum((real)0.5 * (qacc - a0) * (Ma - qfs));
-    real newcost = gauss + mw_constraint_eval(w, lane, false);
+    real newcost = gauss + mw_constraint_eval<SP>(w, lane, false);
     SYNCW();
     real improvement = scale * (cost - newcost);
     cost = newcost;
@@ -921,7 +947,7 @@ __device__ __noinline__ void mw_solve(const MwModel* __restrict__ m, WarpScratch
   }
   // (eF / fn are current: every exit from the loop follows an evaluation at the final point)
   real fc = 0;
-  if (lane < nv) { for (int r = 0; r < nefc; r++) fc += J[r * NVP + lane] * w->eF[r]; w->qacc[lane] = qacc; w->qfrc_con[lane] = fc; }
+  if (lane < nv) { for (int r = 0; r < nefc; r++) fc += JROW(r)[lane] * EV(eF, r); w->qacc[lane] = qacc; w->qfrc_con[lane] = fc; }
   if (lane == 0) w->solver_iter = iter;
   SYNCW();
 }
@@ -952,7 +978,8 @@ __device__ __noinline__ void mw_forward(const MwModel* __restrict__ m, const flo
   PROF_(0, 1)
   mw_collide(m, meshvert, w, lane);
   PROF_(1, 2)
-  mw_make_constraints(m, w, L, lane);
+  const bool spill = w->ncon > MW_SMCON;          // this pass overflowed the shared-memory capacity (warp-uniform, rare)
+  if (spill) mw_make_constraints<true>(m, w, L, lane); else mw_make_constraints<false>(m, w, L, lane);
   PROF_(3, 3)
   real bias = mw_rne_bias(m, w, L, lane);
   // passive + actuation  [mj_passive, mj_fwdActuation]
@@ -976,7 +1003,7 @@ __device__ __noinline__ void mw_forward(const MwModel* __restrict__ m, const flo
   if (lane < nv) w->qacc_smooth[lane] = as;
   SYNCW();
   PROF_(4, 4)
-  mw_solve(m, w, lane, sizeof(real) == 4 ? 8 : 50);
+  if (spill) mw_solve<true>(m, w, lane, sizeof(real) == 4 ? 8 : 50); else mw_solve<false>(m, w, lane, sizeof(real) == 4 ? 8 : 50);
   PROF_(5, 5)
 #undef PROF_
 }

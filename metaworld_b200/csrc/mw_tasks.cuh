@@ -107,7 +107,7 @@ DEV void tcp_center(const TaskCtx& c, real* out) {
 DEV bool touching_object(const TaskCtx& c, int g, int g_lpad, int g_rpad) {
   real lf = 0, rf = 0;
   for (int i = 0; i < c.w->ncon; i++) {
-    const Contact* k = &c.w->con[i];
+    const Contact* k = mw_con(c.w, i);
     if (k->row < 0) continue;
     bool hasobj = k->g1 == g || k->g2 == g;
     if (hasobj && (k->g1 == g_lpad || k->g2 == g_lpad)) lf += k->fn;

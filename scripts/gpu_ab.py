@@ -13,20 +13,22 @@ import numpy as np, torch
 sys.path.insert(0, '.')
 from metaworld_b200.vector_env import make_mt_envs
 from metaworld_b200.engine import lib
-env = make_mt_envs("MT50", seed=42, num_envs=4096, use_one_hot=True)
+BENCH = sys.argv[3] if len(sys.argv) > 3 else "MT50"
+NENV = int(sys.argv[4]) if len(sys.argv) > 4 else 4096
+env = make_mt_envs(BENCH, seed=42, num_envs=NENV, use_one_hot=True)
 env.reset(); env.enable_device_sampler()
 g = torch.Generator(device=env.device); g.manual_seed(3)
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 150
 steps = []
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for t in range(N):
-    a = torch.rand(4096, 4, device=env.device, generator=g) * 2 - 1
+    a = torch.rand(NENV, 4, device=env.device, generator=g) * 2 - 1
     o, r, te, tr, info = env.step_torch(a)
     h = hashlib.sha256(); h.update(o.cpu().numpy().tobytes()); h.update(r.cpu().numpy().tobytes()); h.update(info.cpu().numpy().tobytes())
     steps.append(h.hexdigest())
 torch.cuda.synchronize()
 st = env.engine.get_state()
-acts = [torch.rand(4096, 4, device=env.device, generator=g) * 2 - 1 for _ in range(60)]
+acts = [torch.rand(NENV, 4, device=env.device, generator=g) * 2 - 1 for _ in range(60)]
 e0.record()
 for a in acts:
     env.step_torch(a)

@@ -611,3 +611,28 @@ def test_step_torch_applies_recurrent_obs_and_reward_normalisation_on_device(tor
         assert np.allclose(x[0], y[0].cpu().numpy(), atol=1e-6) and np.allclose(x[1], y[1].cpu().numpy(), atol=1e-9)
         assert np.array_equal(x[2], y[2].cpu().numpy().astype(bool)) and np.array_equal(x[3], y[3].cpu().numpy().astype(bool))
     a.close(); b.close()
+
+
+def test_contact_overflow_path_is_bitwise_identical(torch_cuda, tmp_path):
+    """An env with more contacts / constraint rows than the shared-memory scratch holds keeps them all: the tail goes to
+    global memory and the pass runs the <SP = true> instantiation of the constraint code.  Built with a shared capacity of 6
+    contacts (48 rows) nearly every env takes that path in nearly every pass; obs / reward / info digests of a 120-step MT10
+    rollout and the final device state must equal the standard build's bit for bit."""
+    import json, subprocess, sys
+    from metaworld_b200 import build as B
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    var = B.build_variant(os.path.join(root, "tests", "_build", "libmwb200_smcon6.so"), ["MW_SMCON=6"])
+    outs = []
+    for name, lib in (("std", None), ("smcon6", var)):
+        env = dict(os.environ)
+        if lib:
+            env["MW_B200_LIB"] = lib
+        else:
+            env.pop("MW_B200_LIB", None)
+        out = str(tmp_path / f"{name}.json")
+        r = subprocess.run([sys.executable, os.path.join(root, "scripts", "gpu_ab.py"), out, "120", "MT10", "350"], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append(json.load(open(out)))
+    a, b = outs
+    assert "shared 48" in a["build"] and "shared 6" in b["build"]
+    assert a["steps"] == b["steps"] and a["state"] == b["state"] and a["dropped"] == b["dropped"] == 0
