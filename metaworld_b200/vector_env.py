@@ -289,12 +289,21 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
                          self.d_final_obs, self.d_final_info, self.d_next)
         self.h_small.copy_(self.d_small, non_blocking=True)
         self.h_obs.copy_(self.d_obs, non_blocking=True)
+        # truncations are known in advance (the host mirrors the episode lengths): fetch the terminal rows of those envs in
+        # the same batch of copies, so that a step with finished envs still needs one synchronisation only
+        pred = np.nonzero(self._ep_len + 1 >= min(self.max_episode_steps, MAX_PATH_LENGTH))[0]
+        if len(pred):
+            d_pred = t.from_numpy(pred).to(self.device, non_blocking=True)
+            self.h_final_obs[: len(pred)].copy_(self.d_final_obs.index_select(0, d_pred), non_blocking=True)
+            self.h_final_info[: len(pred)].copy_(self.d_final_info.index_select(0, d_pred), non_blocking=True)
         if self.device.type == "cuda":
             t.cuda.current_stream(self.device).synchronize()
-        sm = self.h_small.numpy()
-        obs = self.h_obs.numpy().astype(self.obs_dtype)          # fresh array every step, like the reference (:637)
-        reward = sm[:, 7].astype(np.float64)
-        flags = sm[:, 8].astype(np.int64)
+        # fresh arrays every step, like the reference (:637).  (single-threaded numpy copies on purpose: torch's parallel host
+        # copies are faster when idle but collapse under a cgroup CPU quota smaller than the machine's core count)
+        obs = self.h_obs.numpy().copy() if self.obs_dtype == np.float32 else self.h_obs.numpy().astype(np.float64)
+        sm = np.ascontiguousarray(self.h_small.numpy().T, dtype=np.float64)      # [9, N]: rows are contiguous per-key arrays
+        reward = sm[7]
+        flags = sm[8].astype(np.int64)
         terminated, truncated = (flags & 1).astype(bool), (flags & 2).astype(bool)
         self._ep_len += 1
         done = terminated | truncated
@@ -305,15 +314,18 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
         live = ~done
         if live.any():
             for i, k in enumerate(INFO_KEYS):
-                infos[k] = np.where(live, sm[:, i], 0.0).astype(np.float64) if any_done else sm[:, i].astype(np.float64)
+                infos[k] = np.where(live, sm[i], 0.0) if any_done else sm[i]
                 infos["_" + k] = live.copy()
         fo = ep_r = None
         if any_done:
             # terminal observations / infos of the finished envs only (a few rows per step in steady state)
             idx = np.nonzero(done)[0]
-            d_idx = t.from_numpy(idx).to(self.device, non_blocking=True)
-            rows_o = self.d_final_obs.index_select(0, d_idx).cpu().numpy()
-            rows_i = self.d_final_info.index_select(0, d_idx).cpu().numpy()
+            if np.array_equal(idx, pred):            # exactly the predicted truncations (always, unless success terminates)
+                rows_o, rows_i = self.h_final_obs[: len(idx)].numpy().copy(), self.h_final_info[: len(idx)].numpy().copy()
+            else:
+                d_idx = t.from_numpy(idx).to(self.device, non_blocking=True)
+                rows_o = self.d_final_obs.index_select(0, d_idx).cpu().numpy()
+                rows_i = self.d_final_info.index_select(0, d_idx).cpu().numpy()
             fo = np.zeros((self.num_envs, self.obs_dim), dtype=self.obs_dtype)
             fo[idx] = rows_o
         if self.post.active:
