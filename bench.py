@@ -69,33 +69,74 @@ def algorithmic_bytes(names):
 
 
 class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons during the timed regions.  NVML (pynvml) is polled every 10 ms, so even the driver's
+    20-step window (~70 ms) gets several samples; `nvidia-smi` (one process per sample, ~50 ms) is the fallback."""
+
+    REASONS = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
     def __init__(self, gpu):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu, [], False
+        self.gpu, self.rows, self.stop_flag, self.active = gpu, [], False, False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(gpu)))
+        except Exception:
+            self.nvml = None
 
-    def run(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        while not self.stop_flag:
+    @staticmethod
+    def _physical_index(local):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                return int(vis.split(",")[local])
             except Exception:
                 pass
-            time.sleep(0.2)
+        return local
 
-    def reset(self):
-        self.rows = []
+    def _sample_nvml(self):
+        nv, h = self.nvml
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        return [float(sm), float(mx)] + [bool(r & bits[k]) for k in self.REASONS]
+
+    def _sample_smi(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        r = [x.strip() for x in out.split(",")]
+        return [float(r[0]), float(r[1])] + [x.lower().startswith("active") for x in r[2:6]]
+
+    def run(self):
+        while not self.stop_flag:
+            if self.active:
+                try:
+                    self.rows.append(self._sample_nvml() if self.nvml else self._sample_smi())
+                except Exception:
+                    pass
+            time.sleep(0.01 if self.nvml else 0.2)
+
+    def begin(self):
+        """start of a timed region (samples outside timed regions are not kept)"""
+        self.active = True
+
+    def end(self):
+        self.active = False
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (nvml and nvidia-smi unavailable)"], "samples": 0}
+        sm = [r[0] for r in self.rows]
+        mx = [r[1] for r in self.rows]
+        reasons = [n for i, n in enumerate(self.REASONS) if any(r[2 + i] for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": reasons, "samples": len(self.rows),
+                "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------- CPU (oracle) timing
@@ -295,6 +336,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    sampler.begin()
     t1 = time.perf_counter()
     n_final = 0
     for i in range(Ke):
@@ -302,6 +344,7 @@ def run_ours(args):
         n_final += int((out[2] | out[3]).sum())
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t1
+    sampler.end()
     # ---- device-resident: actions + state in HBM, device-side task sampler, CUDA events around every step
     gen = torch.Generator(device=dev); gen.manual_seed(args.seed + rank)
     actions = torch.rand(K + W, N, 4, device=dev, generator=gen) * 2 - 1      # resident in HBM before timing
@@ -315,7 +358,6 @@ def run_ours(args):
     for i in range(W):
         env.step_torch(actions[i])
     torch.cuda.synchronize()
-    sampler.reset()
     if world > 1:
         dist.barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
@@ -324,6 +366,7 @@ def run_ours(args):
     ncu_range = os.environ.get("MW_BENCH_NCU") == "1"     # `ncu --profile-from-start off`: capture the timed region only (launch list under profiles/)
     if ncu_range:
         torch.cuda.profiler.start()
+    sampler.begin()
     for i in range(K):
         flush.fill_(float(i))                       # evict L2 between timed iterations (outside the event pair)
         ev[i][0].record()
@@ -342,6 +385,7 @@ def run_ours(args):
     if gather is not None:
         torch.cuda.current_stream(dev).wait_stream(gather[0])
     torch.cuda.synchronize()
+    sampler.end()
     if ncu_range:
         torch.cuda.profiler.stop()
     if world > 1:

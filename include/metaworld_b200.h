@@ -46,8 +46,8 @@ int mw_set_envs(mw_engine*, int n_envs, const int* env_model);
  * rand_vec_pass1 (NULL = same as rand_vec): with an UNFROZEN rand_vec (_make_tasks, the goal_hidden / goal_observable
  * envs, metaworld/env_dict.py:144-152) each reset_model pass draws its own vector; the first pass's one survives in
  * whatever the task's reset_model reads before the next kinematics update (e.g. the stale object pose in the reset obs). */
-int mw_build_snapshots(mw_engine*, int n, const int* model_idx, const float* rand_vec /*[n,6]*/,
-                       const float* rand_vec_pass1 /*[n,6] or NULL*/, const unsigned char* partially_observable,
+int mw_build_snapshots(mw_engine*, int n, const int* model_idx, const double* rand_vec /*[n,6] float64, as in Task.data*/,
+                       const double* rand_vec_pass1 /*[n,6] or NULL*/, const unsigned char* partially_observable,
                        int* snapshot_ids_out);
 /* Appends n snapshot records produced elsewhere (mw_get_snapshots of another engine, e.g. the float64 build of this
  * library, or a checkpoint); same record layout, ids returned like mw_build_snapshots.                           */

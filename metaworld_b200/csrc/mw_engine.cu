@@ -255,7 +255,7 @@ k_step(EngineDev e, const int* __restrict__ block_order, const int* __restrict__
 // builds episode-start snapshots: exact reset() sequence of the reference (reset_model, mj_resetData, reset_model)
 __global__ void __launch_bounds__(BLOCK_THREADS, 1)
 k_snapshot(EngineDev e, const int* __restrict__ block_model, const int* __restrict__ block_start, const int* __restrict__ block_count,
-           const int* __restrict__ perm, const float* __restrict__ rand_vec, const float* __restrict__ rand_vec_pass1, const unsigned char* __restrict__ partial, int snap_base) {
+           const int* __restrict__ perm, const double* __restrict__ rand_vec, const double* __restrict__ rand_vec_pass1, const unsigned char* __restrict__ partial, int snap_base) {
   extern __shared__ __align__(16) unsigned char smem[];
   BlockShared* bs = (BlockShared*)smem;
   WarpShared* wsa = (WarpShared*)(smem + sizeof(BlockShared));
@@ -270,8 +270,8 @@ k_snapshot(EngineDev e, const int* __restrict__ block_model, const int* __restri
   WarpScratch* w = &ws->w;
   join_cta(bs, wsa, w, warp, block_count[blockIdx.x]);
   const MwModel* m = (const MwModel*)bs->model;
-  const float* rv2 = rand_vec + 6 * item;
-  const float* rv1 = rand_vec_pass1 ? rand_vec_pass1 + 6 * item : rv2;   // an unfrozen rand_vec draws once per reset_model pass
+  const double* rv2 = rand_vec + 6 * item;
+  const double* rv1 = rand_vec_pass1 ? rand_vec_pass1 + 6 * item : rv2;   // an unfrozen rand_vec draws once per reset_model pass
   real act[4] = {0, 0, 0, 0};
   TaskCtx c; c.m = m; c.tc = &bs->tc; c.w = w; c.s = &ws->es; c.action = act; c.meshvert = e.meshverts[mi];
   for (int i = lane; i < 128; i += 32) ((float*)&ws->es)[i] = 0.f;
@@ -613,7 +613,7 @@ int mw_set_envs(mw_engine* E, int n_envs, const int* env_model) {
   return MW_OK;
 }
 
-int mw_build_snapshots(mw_engine* E, int n, const int* model_idx, const float* rand_vec, const float* rand_vec_pass1, const unsigned char* partial, int* ids_out) {
+int mw_build_snapshots(mw_engine* E, int n, const int* model_idx, const double* rand_vec, const double* rand_vec_pass1, const unsigned char* partial, int* ids_out) {
   if (!E || n <= 0 || !model_idx || !rand_vec || !partial) return fail(MW_ERR_ARG, "mw_build_snapshots: bad arguments");
   CK(cudaSetDevice(E->device));
   if (E->n_snaps + n > E->snap_cap) {
@@ -627,12 +627,12 @@ int mw_build_snapshots(mw_engine* E, int n, const int* model_idx, const float* r
   for (int v : im) if (v < 0 || v >= E->n_models) return fail(MW_ERR_ARG, "mw_build_snapshots: model index out of range");
   make_blocks(E->n_models, im, bm, bs, bc, perm);
   if (ensure_epa(E, bm.size())) return MW_ERR_CUDA;
-  int *d_bm = nullptr, *d_bs = nullptr, *d_bc = nullptr, *d_perm = nullptr; float* d_rv = nullptr; unsigned char* d_po = nullptr;
+  int *d_bm = nullptr, *d_bs = nullptr, *d_bc = nullptr, *d_perm = nullptr; double* d_rv = nullptr; unsigned char* d_po = nullptr;
   if (upload(&d_bm, bm) || upload(&d_bs, bs) || upload(&d_bc, bc) || upload(&d_perm, perm)) return MW_ERR_CUDA;
-  CK(cudaMalloc((void**)&d_rv, sizeof(float) * 6 * n)); CK(cudaMemcpy(d_rv, rand_vec, sizeof(float) * 6 * n, cudaMemcpyHostToDevice));
+  CK(cudaMalloc((void**)&d_rv, sizeof(double) * 6 * n)); CK(cudaMemcpy(d_rv, rand_vec, sizeof(double) * 6 * n, cudaMemcpyHostToDevice));
   CK(cudaMalloc((void**)&d_po, n)); CK(cudaMemcpy(d_po, partial, n, cudaMemcpyHostToDevice));
-  float* d_rv1 = nullptr;
-  if (rand_vec_pass1) { CK(cudaMalloc((void**)&d_rv1, sizeof(float) * 6 * n)); CK(cudaMemcpy(d_rv1, rand_vec_pass1, sizeof(float) * 6 * n, cudaMemcpyHostToDevice)); }
+  double* d_rv1 = nullptr;
+  if (rand_vec_pass1) { CK(cudaMalloc((void**)&d_rv1, sizeof(double) * 6 * n)); CK(cudaMemcpy(d_rv1, rand_vec_pass1, sizeof(double) * 6 * n, cudaMemcpyHostToDevice)); }
   k_snapshot<<<(int)bm.size(), BLOCK_THREADS, smem_bytes()>>>(E->dev(), d_bm, d_bs, d_bc, d_perm, d_rv, d_rv1, d_po, E->n_snaps);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());

@@ -260,8 +260,10 @@ DEV real mw_chol(real* A, int nv, int lane) {
       a[j] = lij;
 #pragma unroll
       for (int k = j + 1; k < MW_MAXDOF; k++) {
-        const real lkj = bcast(lij, k);                      // L[k][j]
-        if (k <= lane) a[k] -= lij * lkj;
+        if (k < nv) {                                        // (uniform: 20 of the 50 models have nv = 10)
+          const real lkj = bcast(lij, k);                    // L[k][j]
+          if (k <= lane) a[k] -= lij * lkj;
+        }
       }
     }
   }

@@ -768,7 +768,7 @@ DEV void task_reward(const TaskCtx& c, const real* obs, real* reward, real* info
 
 // ---------------------------------------------------------------- reset_model (after _reset_hand); all lanes call
 // rv = the task's frozen rand_vec (Task.data['rand_vec']); writes env constants into c.s (lane 0)
-DEV void task_reset_model(const TaskCtx& c, const float* rv, int lane) {
+DEV void task_reset_model(const TaskCtx& c, const double* rv, int lane) {
   switch (c.tc->task_id) {
     case T_REACH: {   // sawyer_reach_v3.py:119-138
       real p[3] = {rv[0], rv[1], rv[2]};

@@ -184,7 +184,7 @@ class Engine:
         mi = np.ascontiguousarray(model_idx, dtype=np.int32)
 
         def pack(v):
-            out = np.zeros((len(mi), 6), dtype=np.float32)
+            out = np.zeros((len(mi), 6), dtype=np.float64)     # the goal vector stays float64 from Task.data to the device
             v = np.asarray(v, dtype=np.float64).reshape(len(mi), -1)
             out[:, : v.shape[1]] = v
             return out

@@ -59,3 +59,24 @@ def test_steppost_matches_scalar_wrappers():
                     assert np.allclose(o[i], s.reset(reset_obs[i]))
                 else:
                     assert np.allclose(o[i], so) and fin[i] == 0.0
+
+
+def test_torch_variant_equals_numpy_variant():
+    """post.StepPostTorch (what step_torch applies on the device) against post.StepPost, on CPU tensors."""
+    import torch
+    from metaworld_b200.post import StepPost, StepPostTorch
+    n, d = 6, 9
+    rng = np.random.default_rng(3)
+    a = StepPost(n, True, True, "exponential", 0.05)
+    b = StepPostTorch(torch, torch.device("cpu"), n, d, True, True, "exponential", 0.05)
+    o0 = rng.normal(size=(n, d)).astype(np.float32)
+    assert np.array_equal(a.on_reset(o0), b.on_reset(torch.from_numpy(o0)).numpy())
+    for t in range(12):
+        obs = rng.normal(size=(n, d)).astype(np.float32); fo = rng.normal(size=(n, d)).astype(np.float32)
+        act = rng.uniform(-1, 1, size=(n, 4)).astype(np.float32); rew = rng.uniform(0, 10, size=n)
+        term = rng.random(n) < 0.1; trunc = (t % 5 == 4) & ~term
+        x = a.on_step(obs, act, rew, term, trunc, final_obs=fo)
+        y = b.on_step(torch.from_numpy(obs), torch.from_numpy(act), torch.from_numpy(rew.astype(np.float32)), torch.from_numpy(term), torch.from_numpy(trunc), torch.from_numpy(fo))
+        r32 = rew.astype(np.float32).astype(np.float64)       # the device path sees the float32 reward
+        assert np.allclose(x[0], y[0].numpy(), atol=1e-6) and np.allclose(x[2], y[2].numpy(), atol=1e-6)
+        assert np.allclose(x[1], y[1].numpy(), rtol=1e-5) and np.allclose(x[3], y[3].numpy(), rtol=1e-5, atol=1e-6)
