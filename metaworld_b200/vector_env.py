@@ -110,8 +110,6 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
                  normalize_observations=False, checkpoint_env_ids=None, type_seeds=None, **unused):
         if reward_function_version != "v2":
             raise NotImplementedError("only the default v2 rewards are implemented on the device")
-        if normalize_observations:
-            raise NotImplementedError("normalize_observations relies on gymnasium.wrappers.NormalizeObservation; not provided")
         n_types = len(env_names)
         num_envs = n_types if num_envs is None else int(num_envs)
         if num_envs < n_types:
@@ -197,10 +195,15 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
         self._device_sampler = False
         # optional per-sub-env wrappers of the reference that sit above the one-hot wrapper (metaworld/__init__.py:437-444)
         from .post import StepPost
-        self.post = StepPost(N, recurrent_info_in_obs, normalize_reward_in_recurrent_info, reward_normalization_method, reward_alpha)
+        self.post = StepPost(N, recurrent_info_in_obs, normalize_reward_in_recurrent_info, reward_normalization_method, reward_alpha,
+                             normalize_observations)
         if self.post.recurrent:     # RNNBasedMetaRLWrapper's space: unbounded float32 of obs + action + reward + done (wrappers.py:55-62)
             D = self.obs_dim + self.post.extra
             self.obs_dtype = np.float32
+            self.single_observation_space = _gym.Box(np.full(D, -np.inf, np.float32), np.full(D, np.inf, np.float32), dtype=np.float32)
+            self.observation_space = _gym.batch_space(self.single_observation_space, num_envs)
+        if self.post.norm_obs:      # gymnasium.wrappers.NormalizeObservation: unbounded float32 space of the same shape
+            D = self.obs_dim + self.post.extra
             self.single_observation_space = _gym.Box(np.full(D, -np.inf, np.float32), np.full(D, np.inf, np.float32), dtype=np.float32)
             self.observation_space = _gym.batch_space(self.single_observation_space, num_envs)
 
@@ -384,7 +387,7 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
             from .post import StepPostTorch
             p = self.post
             self._ptorch = StepPostTorch(self.torch, self.device, self.num_envs, self.obs_dim, p.recurrent, p.norm_in_obs,
-                                         "exponential" if p.exponential else None, p.alpha)
+                                         "exponential" if p.exponential else "gymnasium" if p.gym_reward else None, p.alpha, p.norm_obs)
             self._ptorch.load_host_state(p)
         return self._ptorch
 

@@ -98,7 +98,10 @@ class NormalizeReward(Wrapper):
 class NormalizeObservation(ObservationWrapper):
     def __init__(self, env, epsilon=1e-8):
         super().__init__(env)
-        self.obs_rms = RunningMeanStd(shape=self.observation_space.shape, dtype=self.observation_space.dtype)
+        from ..spaces import Box
+        shape = env.observation_space.shape
+        self.observation_space = Box(low=-np.inf, high=np.inf, shape=shape, dtype=np.float32)
+        self.obs_rms = RunningMeanStd(shape=shape, dtype=np.float32)
         self.epsilon, self._update_running_mean = epsilon, True
 
     def observation(self, observation):

@@ -120,6 +120,22 @@ def test_ml10_train_pseudorandom_partially_observable_matches_reference_stack(gy
     assert not o1[:, 36:].any() and not o2[:, 36:].any()
 
 
+@pytest.mark.parametrize("extra", [dict(reward_normalization_method="gymnasium", normalize_observations=True),
+                                   dict(recurrent_info_in_obs=True, normalize_observations=True, reward_normalization_method="exponential"),
+                                   dict(recurrent_info_in_obs=True, normalize_reward_in_recurrent_info=False, reward_normalization_method="gymnasium")])
+def test_normalisation_and_recurrent_wrappers_match_reference_stack(gym, extra):
+    """The non-default per-sub-env wrappers of metaworld/__init__.py:437-446, autoresets included (the observation
+    statistics see the terminal AND the reset observation of a finished env; the discounted return survives truncation)."""
+    kw = dict(seed=11, use_one_hot=True, max_episode_steps=7, terminate_on_success=True, num_goals=2, **extra)
+    ref = gym.make_vec("Meta-World/MT10", vector_strategy="sync", **kw)
+    ours = _ours("mt", "MT10", **kw)
+    assert ref.single_observation_space.shape == ours.single_observation_space.shape
+    assert ref.single_observation_space.dtype == ours.single_observation_space.dtype
+    # both sides run the same float64 physics, but ours passes observations through the engine interface as float32: the
+    # 1e-7 rounding is amplified by 1 / sqrt(var) of slowly varying features
+    assert _compare_rollout(ref, ours, 25, seed=4, atol=3e-4) >= 30
+
+
 def test_mt1_single_task_vector_and_explicit_resets(gym):
     import metaworld
     kw = dict(seed=3, max_episode_steps=6)
