@@ -180,10 +180,12 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
         self.d_actions = torch.zeros(N, 4, device=dev)
         self.d_next = torch.zeros(N, dtype=torch.int32, device=dev)
         self.d_cur = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.d_idx = torch.zeros(N, dtype=torch.int64, device=dev)
         on_gpu = self.device.type == "cuda"      # (the host-logic tests drive this class with a CPU stand-in for the engine)
         pin = (lambda t: t.pin_memory()) if on_gpu else (lambda t: t)
         self.h_actions = pin(torch.zeros(N, 4))
         self.h_next = pin(torch.zeros(N, dtype=torch.int32))
+        self.h_idx = pin(torch.zeros(N, dtype=torch.int64))
         self.h_obs = pin(torch.zeros(N, self.obs_dim))
         self.h_small = pin(torch.zeros(N, 9))
         self.h_final_obs = pin(torch.zeros(N, self.obs_dim))
@@ -278,6 +280,15 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
             obs = self.post.on_reset(obs)
         return obs, {}
 
+    def _advance_streams(self, idx):
+        """The autoreset's task-select draw of sub-envs `idx` (their episode ends with this step): the speculative draw
+        becomes the running task and the draw for the episode after it is made."""
+        for e in idx:
+            s = self.sub[e]
+            s.current_task, s._pre = s.pending, None
+            self._draw_pending(e)
+        self._push_next()
+
     def step(self, actions):
         if self._needs_reset:
             raise RuntimeError("reset() must be called before step()")
@@ -285,77 +296,86 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
             raise RuntimeError("the device-side task sampler is active (step_torch was used): the numpy step API and its host "
                                "task streams are no longer in sync; call disable_device_sampler() + reset() first")
         t = self.torch
-        a = np.ascontiguousarray(actions, dtype=np.float32).reshape(self.num_envs, 4)
+        N = self.num_envs
+        a = np.ascontiguousarray(actions, dtype=np.float32).reshape(N, 4)
         self.h_actions.copy_(t.from_numpy(a))
         self.d_actions.copy_(self.h_actions, non_blocking=True)
         self.engine.step(self.d_actions, self.d_obs, self.d_reward, self.d_term, self.d_trunc, self.d_small,
                          self.d_final_obs, self.d_final_info, self.d_next)
         self.h_small.copy_(self.d_small, non_blocking=True)
         self.h_obs.copy_(self.d_obs, non_blocking=True)
-        # truncations are known in advance (the host mirrors the episode lengths): fetch the terminal rows of those envs in
-        # the same batch of copies, so that a step with finished envs still needs one synchronisation only
+        # ---- while the kernel runs: everything that does not need its results.
+        # Truncations are known in advance (the host mirrors the episode lengths): the terminal rows of those envs are
+        # fetched in the same batch of copies, their task streams are advanced and the snapshot ids of the episodes after
+        # the coming ones are queued behind the kernel (stream order: k_step reads d_next before this copy overwrites it).
         pred = np.nonzero(self._ep_len + 1 >= min(self.max_episode_steps, MAX_PATH_LENGTH))[0]
-        if len(pred):
-            d_pred = t.from_numpy(pred).to(self.device, non_blocking=True)
-            self.h_final_obs[: len(pred)].copy_(self.d_final_obs.index_select(0, d_pred), non_blocking=True)
-            self.h_final_info[: len(pred)].copy_(self.d_final_info.index_select(0, d_pred), non_blocking=True)
+        npred = len(pred)
+        if npred:
+            self.h_idx[:npred] = t.from_numpy(pred)
+            d_pred = self.d_idx[:npred]
+            d_pred.copy_(self.h_idx[:npred], non_blocking=True)
+            self.h_final_obs[:npred].copy_(self.d_final_obs.index_select(0, d_pred), non_blocking=True)
+            self.h_final_info[:npred].copy_(self.d_final_info.index_select(0, d_pred), non_blocking=True)
+            self._advance_streams(pred)
+        obs = np.empty((N, self.obs_dim), dtype=self.obs_dtype)        # fresh arrays every step, like the reference (:637);
+        obs[:] = 0                                                        # allocated and touched here, off the critical path
         if self.device.type == "cuda":
             t.cuda.current_stream(self.device).synchronize()
-        # fresh arrays every step, like the reference (:637).  (single-threaded numpy copies on purpose: torch's parallel host
-        # copies are faster when idle but collapse under a cgroup CPU quota smaller than the machine's core count)
-        obs = self.h_obs.numpy().copy() if self.obs_dtype == np.float32 else self.h_obs.numpy().astype(np.float64)
+        # ---- results (single-threaded numpy on purpose: torch's parallel host copies are faster when idle but collapse
+        # under a cgroup CPU quota smaller than the machine's core count)
+        np.copyto(obs, self.h_obs.numpy())
         sm = np.ascontiguousarray(self.h_small.numpy().T, dtype=np.float64)      # [9, N]: rows are contiguous per-key arrays
         reward = sm[7]
-        flags = sm[8].astype(np.int64)
+        flags = sm[8].astype(np.int8)
         terminated, truncated = (flags & 1).astype(bool), (flags & 2).astype(bool)
         self._ep_len += 1
         done = terminated | truncated
-        any_done = bool(done.any())
+        idx = np.nonzero(done)[0]
+        any_done = len(idx) > 0
         # SAME_STEP (gymnasium SyncVectorEnv): a finished env's step info moves to `final_info` and its slot in the
         # top-level arrays is the (empty) reset info -> value 0, mask False; keys vanish when every env finished
         infos = {}
-        live = ~done
-        if live.any():
+        if len(idx) < N:
+            live = ~done
             for i, k in enumerate(INFO_KEYS):
-                infos[k] = np.where(live, sm[i], 0.0) if any_done else sm[i]
+                v = sm[i]
+                if any_done:
+                    v[idx] = 0.0
+                infos[k] = v
                 infos["_" + k] = live.copy()
         fo = ep_r = None
         if any_done:
             # terminal observations / infos of the finished envs only (a few rows per step in steady state)
-            idx = np.nonzero(done)[0]
             if np.array_equal(idx, pred):            # exactly the predicted truncations (always, unless success terminates)
-                rows_o, rows_i = self.h_final_obs[: len(idx)].numpy().copy(), self.h_final_info[: len(idx)].numpy().copy()
+                rows_o, rows_i = self.h_final_obs[:npred].numpy().copy(), self.h_final_info[:npred].numpy().copy()
             else:
                 d_idx = t.from_numpy(idx).to(self.device, non_blocking=True)
                 rows_o = self.d_final_obs.index_select(0, d_idx).cpu().numpy()
                 rows_i = self.d_final_info.index_select(0, d_idx).cpu().numpy()
-            fo = np.zeros((self.num_envs, self.obs_dim), dtype=self.obs_dtype)
+            fo = np.zeros((N, self.obs_dim), dtype=self.obs_dtype)
             fo[idx] = rows_o
         if self.post.active:
             obs, reward, fo, ep_r = self.post.on_step(obs, a, reward, terminated, truncated, final_obs=fo)
         if any_done:
-            fi = np.zeros((self.num_envs, 8), dtype=np.float32)
-            fi[idx] = rows_i
+            fi = np.zeros((8, N))
+            fi[:, idx] = rows_i.T
             if ep_r is not None:
-                fi[:, 7] = ep_r          # RecordEpisodeStatistics sits outside the reward normalisation
-            final_obs = np.full(self.num_envs, None, dtype=object)
+                fi[7] = ep_r             # RecordEpisodeStatistics sits outside the reward normalisation
+            final_obs = np.full(N, None, dtype=object)
             for e in idx:
                 final_obs[e] = fo[e]
             final_info = {}
             for i, k in enumerate(INFO_KEYS):
-                final_info[k] = fi[:, i].astype(np.float64)        # rows of unfinished envs are 0
+                final_info[k] = fi[i]                              # rows of unfinished envs are 0
                 final_info["_" + k] = done.copy()
-            final_info["episode"] = {"r": fi[:, 7].astype(np.float64), "l": np.where(done, self._ep_len, 0),
-                                     "t": np.zeros(self.num_envs), "_r": done.copy(), "_l": done.copy(), "_t": done.copy()}
+            final_info["episode"] = {"r": fi[7], "l": np.where(done, self._ep_len, 0),
+                                     "t": np.zeros(N), "_r": done.copy(), "_l": done.copy(), "_t": done.copy()}
             final_info["_episode"] = done.copy()
             infos["final_obs"], infos["_final_obs"] = final_obs, done.copy()
             infos["final_info"], infos["_final_info"] = final_info, done.copy()
-            for e in idx:
-                s = self.sub[e]
-                s.current_task, s._pre = s.pending, None      # the autoreset's task-select draw has now happened
-                self._draw_pending(e)
-                self._ep_len[e] = 0
-            self._push_next()
+            self._ep_len[idx] = 0
+            if npred < len(idx):                     # terminations nobody could predict (terminate_on_success)
+                self._advance_streams(np.setdiff1d(idx, pred))
         return obs, reward, terminated, truncated, infos
 
     def step_async(self, actions):
