@@ -35,14 +35,22 @@ struct EngineDev {
   MwEnvState* state; MwSnapshot* snaps;
   const int* goal_first; const int* goal_count;      // device sampler ranges (may be NULL)
   int* diag;                                         // [n_envs][3]: contacts dropped, solver iterations, MW_FAULT_* bits (OR)
-  EpaWs* epa;                                        // GJK/EPA polytope workspace, one per launched warp (global memory)
-  WarpSpill* spill;                                  // overflow contacts / constraint rows, one block per launched warp (global memory)
+  EpaWs* epa;                                        // GJK/EPA polytope workspace, one per warp slot (global memory, see scratch_slot)
+  WarpSpill* spill;                                  // overflow contacts / constraint rows, one block per warp slot (global memory)
+  int slot_by_sm;                                    // warp slots are numbered by SM (one resident CTA per SM) instead of by CTA
   unsigned long long* prof;                          // [16] summed cycle / event counters (mw_get_profile)
   unsigned long long* model_cycles;                  // [n_models][2]: warp cycles, env steps (drives mw_rebalance)
   unsigned* env_cost;                                // [n_envs] warp cycles of each env's previous step (drives the launch order)
   unsigned* env_prof;                                // optional [n_envs][16] per-env phase cycles / event counts of the last step (mw_set_profiling)
   int n_envs, max_steps, terminate_on_success; unsigned long long seed;
 };
+
+// The per-warp global scratch (EPA polytope, overflow rows) is addressed by SM, not by CTA, when at most one CTA fits an SM:
+// 148 x WARPS_PER_BLOCK blocks that successive CTAs of an SM reuse stay resident in L2, whereas one block per launched warp
+// (4200 x 10.7 KB for 4096 envs) is a stream of first-touch lines that all end up in DRAM.
+DEV unsigned mw_smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+DEV size_t scratch_slot(const EngineDev& e, int warp) { return (size_t)(e.slot_by_sm ? mw_smid() : blockIdx.x) * WARPS_PER_BLOCK + warp; }
+__global__ void k_nsmid(unsigned* out) { unsigned r; asm volatile("mov.u32 %0, %%nsmid;" : "=r"(r)); *out = r; }
 
 // ---------------------------------------------------------------- shared memory carve-up
 struct BlockShared {
@@ -151,8 +159,8 @@ k_step(EngineDev e, const int* __restrict__ block_order, const int* __restrict__
   if (warp >= block_count[blk]) return;
   const int env = perm[block_start[blk] + warp];
   WarpShared* ws = wsa + warp;
-  ws->w.epa = e.epa + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp);
-  ws->w.sp = e.spill + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp);
+  ws->w.epa = e.epa + scratch_slot(e, warp);
+  ws->w.sp = e.spill + scratch_slot(e, warp);
   WarpScratch* w = &ws->w;
   join_cta(bs, wsa, w, warp, block_count[blk]);
   const MwModel* m = (const MwModel*)bs->model;
@@ -265,8 +273,8 @@ k_snapshot(EngineDev e, const int* __restrict__ block_model, const int* __restri
   if (warp >= block_count[blockIdx.x]) return;
   const int item = perm[block_start[blockIdx.x] + warp];
   WarpShared* ws = wsa + warp;
-  ws->w.epa = e.epa + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp);
-  ws->w.sp = e.spill + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp);
+  ws->w.epa = e.epa + scratch_slot(e, warp);
+  ws->w.sp = e.spill + scratch_slot(e, warp);
   WarpScratch* w = &ws->w;
   join_cta(bs, wsa, w, warp, block_count[blockIdx.x]);
   const MwModel* m = (const MwModel*)bs->model;
@@ -337,8 +345,8 @@ k_substeps(EngineDev e, const int* __restrict__ block_model, const int* __restri
   if (warp >= block_count[blockIdx.x]) return;
   const int env = perm[block_start[blockIdx.x] + warp];
   WarpShared* ws = wsa + warp;
-  ws->w.epa = e.epa + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp);
-  ws->w.sp = e.spill + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp);
+  ws->w.epa = e.epa + scratch_slot(e, warp);
+  ws->w.sp = e.spill + scratch_slot(e, warp);
   join_cta(bs, wsa, &ws->w, warp, block_count[blockIdx.x]);
   const MwModel* m = (const MwModel*)bs->model;
   load_env(ws, e.state + env, lane);
@@ -377,8 +385,8 @@ k_evaluate(EngineDev e, const int* __restrict__ block_model, const int* __restri
   if (warp >= block_count[blockIdx.x]) return;
   const int env = perm[block_start[blockIdx.x] + warp];
   WarpShared* ws = wsa + warp;
-  ws->w.epa = e.epa + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp);
-  ws->w.sp = e.spill + ((size_t)blockIdx.x * WARPS_PER_BLOCK + warp);
+  ws->w.epa = e.epa + scratch_slot(e, warp);
+  ws->w.sp = e.spill + scratch_slot(e, warp);
   WarpScratch* w = &ws->w;
   join_cta(bs, wsa, w, warp, block_count[blockIdx.x]);
   const MwModel* m = (const MwModel*)bs->model;
@@ -456,7 +464,7 @@ struct mw_engine {
   std::vector<float*> meshbufs;
   MwEnvState* d_state = nullptr; MwSnapshot* d_snaps = nullptr; int snap_cap = 0, n_snaps = 0;
   int *d_goal_first = nullptr, *d_goal_count = nullptr, *d_diag = nullptr;
-  EpaWs* d_epa = nullptr; WarpSpill* d_spill = nullptr; size_t epa_cap = 0;
+  EpaWs* d_epa = nullptr; WarpSpill* d_spill = nullptr; size_t epa_cap = 0; int slot_by_sm = 0, nsmid = 0;
   unsigned long long* d_prof = nullptr; unsigned long long* d_model_cycles = nullptr; unsigned* d_env_prof = nullptr; int profiling = 0;
   unsigned* d_env_cost = nullptr; int *d_block_order = nullptr, *d_model_first = nullptr, *d_model_count = nullptr; int n_sorted_models = 0;
   std::vector<int> h_faults;                                   // fault bits already drained from d_diag by mw_get_counters
@@ -467,7 +475,7 @@ struct mw_engine {
   unsigned long long launches = 0, env_steps = 0;
   EngineDev dev() const {
     EngineDev e; e.models = d_models; e.model_stride = model_stride; e.taskconsts = d_tc; e.meshverts = d_meshptrs;
-    e.state = d_state; e.snaps = d_snaps; e.goal_first = d_goal_first; e.goal_count = d_goal_count; e.diag = d_diag; e.epa = d_epa; e.spill = d_spill; e.prof = profiling ? d_prof : nullptr; e.model_cycles = d_model_cycles; e.env_cost = d_env_cost; e.env_prof = profiling ? d_env_prof : nullptr;
+    e.state = d_state; e.snaps = d_snaps; e.goal_first = d_goal_first; e.goal_count = d_goal_count; e.diag = d_diag; e.epa = d_epa; e.spill = d_spill; e.slot_by_sm = slot_by_sm; e.prof = profiling ? d_prof : nullptr; e.model_cycles = d_model_cycles; e.env_cost = d_env_cost; e.env_prof = profiling ? d_env_prof : nullptr;
     e.n_envs = n_envs; e.max_steps = max_steps; e.terminate_on_success = terminate_on_success; e.seed = seed; return e;
   }
 };
@@ -487,7 +495,17 @@ static void make_blocks(int n_models, const std::vector<int>& item_model, std::v
   }
 }
 static int ensure_epa(mw_engine* E, size_t n_blocks) {
-  size_t need = n_blocks * WARPS_PER_BLOCK;
+  if (E->nsmid == 0) {
+    // one CTA per SM whenever two CTAs' shared memory cannot fit (true for every build so far: 190-227 KB per CTA)
+    int dev = 0; cudaDeviceProp pr; CK(cudaGetDevice(&dev)); CK(cudaGetDeviceProperties(&pr, dev));
+    unsigned* d_n = nullptr; unsigned h_n = 0;
+    CK(cudaMalloc((void**)&d_n, sizeof(unsigned)));
+    k_nsmid<<<1, 1>>>(d_n);
+    CK(cudaMemcpy(&h_n, d_n, sizeof(unsigned), cudaMemcpyDeviceToHost)); cudaFree(d_n);
+    E->nsmid = (int)h_n;
+    E->slot_by_sm = (2 * smem_bytes() > (size_t)pr.sharedMemPerMultiprocessor && h_n > 0 && h_n <= 4096) ? 1 : 0;
+  }
+  size_t need = (E->slot_by_sm ? (size_t)E->nsmid : n_blocks) * WARPS_PER_BLOCK;
   if (need <= E->epa_cap) return 0;
   if (E->d_epa) cudaFree(E->d_epa);
   if (E->d_spill) cudaFree(E->d_spill);

@@ -275,7 +275,10 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
         self.engine.reset(self.d_cur, self.d_obs)
         self._ep_len[:] = 0
         self._needs_reset = False
-        obs = self.d_obs.cpu().numpy().astype(self.obs_dtype)
+        self.h_obs.copy_(self.d_obs)
+        obs = self.h_obs.numpy().astype(self.obs_dtype)
+        self._obs_template = obs.copy()        # constant columns (one-hot task id) of every later observation; see step()
+        self._obs_template[:, :39] = 0
         if self.post.active:
             obs = self.post.on_reset(obs)
         return obs, {}
@@ -317,13 +320,15 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
             self.h_final_obs[:npred].copy_(self.d_final_obs.index_select(0, d_pred), non_blocking=True)
             self.h_final_info[:npred].copy_(self.d_final_info.index_select(0, d_pred), non_blocking=True)
             self._advance_streams(pred)
-        obs = np.empty((N, self.obs_dim), dtype=self.obs_dtype)        # fresh arrays every step, like the reference (:637);
-        obs[:] = 0                                                        # allocated and touched here, off the critical path
+        # fresh arrays every step, like the reference (:637).  The array is allocated here, off the critical path, as a copy
+        # of a template that already holds the constant columns (the one-hot task id): only the 39 columns the kernel writes
+        # remain to be converted once the results are there
+        obs = self._obs_template.copy()
         if self.device.type == "cuda":
             t.cuda.current_stream(self.device).synchronize()
         # ---- results (single-threaded numpy on purpose: torch's parallel host copies are faster when idle but collapse
         # under a cgroup CPU quota smaller than the machine's core count)
-        np.copyto(obs, self.h_obs.numpy())
+        np.copyto(obs[:, :39], self.h_obs.numpy()[:, :39])
         sm = np.ascontiguousarray(self.h_small.numpy().T, dtype=np.float64)      # [9, N]: rows are contiguous per-key arrays
         reward = sm[7]
         flags = sm[8].astype(np.int8)
@@ -352,18 +357,22 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
                 d_idx = t.from_numpy(idx).to(self.device, non_blocking=True)
                 rows_o = self.d_final_obs.index_select(0, d_idx).cpu().numpy()
                 rows_i = self.d_final_info.index_select(0, d_idx).cpu().numpy()
-            fo = np.zeros((N, self.obs_dim), dtype=self.obs_dtype)
-            fo[idx] = rows_o
+            rows_o = rows_o.astype(self.obs_dtype, copy=False)
         if self.post.active:
+            if any_done:
+                fo = np.zeros((N, self.obs_dim), dtype=self.obs_dtype)
+                fo[idx] = rows_o
             obs, reward, fo, ep_r = self.post.on_step(obs, a, reward, terminated, truncated, final_obs=fo)
+            if any_done:
+                rows_o = fo[idx]
         if any_done:
             fi = np.zeros((8, N))
             fi[:, idx] = rows_i.T
             if ep_r is not None:
                 fi[7] = ep_r             # RecordEpisodeStatistics sits outside the reward normalisation
             final_obs = np.full(N, None, dtype=object)
-            for e in idx:
-                final_obs[e] = fo[e]
+            for j, e in enumerate(idx):
+                final_obs[e] = rows_o[j]
             final_info = {}
             for i, k in enumerate(INFO_KEYS):
                 final_info[k] = fi[i]                              # rows of unfinished envs are 0

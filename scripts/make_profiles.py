@@ -91,3 +91,23 @@ with open(os.path.join(P, f"{R}_parity.md"), "w") as f:
     for l in xf: f.write(f"* `{l}`\n")
 print(open(os.path.join(P, f"{R}_launches_summary.csv")).read())
 print(open(os.path.join(P, f"{R}_k_step_ncu_summary.csv")).read())
+
+# ---- static SASS summary of the shipped library, per kernel (cuobjdump; no GPU needed)
+import re, subprocess
+so = os.path.join(os.path.dirname(P), "metaworld_b200", "libmwb200.so")
+if os.path.exists(so):
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+    res = subprocess.run(["cuobjdump", "--dump-resource-usage", so], capture_output=True, text=True).stdout
+    usage = dict(re.findall(r"Function (\S+):\n\s+(REG:\d+ STACK:\d+ SHARED:\d+)", res))
+    parts = re.split(r"\n\s+Function : (\S+)\n", sass)
+    keys = ["FFMA", "DFMA", "STL", "LDL", "LDS", "STS", "SHFL", "WARPSYNC", "BAR.SYNC", "MUFU", "UBLKCP", "SYNCS"]
+    with open(os.path.join(P, f"{R}_sass_summary.md"), "w") as f:
+        f.write("# Static SASS instruction counts per kernel of `metaworld_b200/libmwb200.so` (sm_100a; `cuobjdump -sass`)\n\n")
+        f.write("`UBLKCP` + `SYNCS` = TMA bulk copy of the model blob + mbarrier.  `k_step` is the kernel the bench times; `k_snapshot` "
+                "(reset double pass), `k_substeps` (diagnostics) and `k_evaluate` (single-env `evaluate_state`) instantiate the same physics.\n\n")
+        f.write("| kernel | instructions | " + " | ".join(keys) + " | resources |\n|---|---|" + "---|" * (len(keys) + 1) + "\n")
+        for name, body in zip(parts[1::2], parts[2::2]):
+            n = len(re.findall(r"/\*[0-9a-f]{4,}\*/", body))
+            mm = re.match(r"_Z(\d+)", name); short = name[len(mm.group(0)):][: int(mm.group(1))] if mm else name
+            f.write(f"| `{short}` | {n} | " + " | ".join(str(len(re.findall(r"\b" + re.escape(k), body))) for k in keys) + f" | {usage.get(name, '')} |\n")
+    print(open(os.path.join(P, f"{R}_sass_summary.md")).read())
