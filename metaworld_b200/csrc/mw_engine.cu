@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -40,7 +41,8 @@ struct EngineDev {
   int slot_by_sm;                                    // warp slots are numbered by SM (one resident CTA per SM) instead of by CTA
   unsigned long long* prof;                          // [16] summed cycle / event counters (mw_get_profile)
   unsigned long long* model_cycles;                  // [n_models][2]: warp cycles, env steps (drives mw_rebalance)
-  unsigned* env_cost;                                // [n_envs] warp cycles of each env's previous step (drives the launch order)
+  unsigned* env_cost;                                // [n_envs] solver work of each env's previous step (orders the envs of a model, k_order_envs)
+  unsigned* env_cycles;                              // [n_envs] cycles each env's warp spent in its previous k_step = duration of its CTA (orders the CTAs, k_order_blocks)
   unsigned* env_prof;                                // optional [n_envs][16] per-env phase cycles / event counts of the last step (mw_set_profiling)
   int n_envs, max_steps, terminate_on_success; unsigned long long seed;
 };
@@ -169,6 +171,7 @@ k_step(EngineDev e, const int* __restrict__ block_order, const int* __restrict__
   if (lane == 0) { w->fault = 0; w->prof_on = e.prof != nullptr; }
   SYNCW();
   const long long t_begin = MW_CLK(w);
+  const long long t_cta = e.env_cycles ? mw_clock() : 0ll;
   real act[4];
   for (int i = 0; i < 4; i++) act[i] = fmin(fmax((real)actions[4 * env + i], (real)-1), (real)1);
   TaskCtx c; c.m = m; c.tc = &bs->tc; c.w = w; c.s = &ws->es; c.action = act; c.meshvert = e.meshverts[mi];
@@ -217,6 +220,7 @@ k_step(EngineDev e, const int* __restrict__ block_order, const int* __restrict__
     const long long own = w->prof[8] - w->prof[12];
     // (a work estimate from counters rather than the cycle clock: Newton iterations weighted by the rows they touch)
     e.env_cost[env] = (unsigned)solver_work;
+    if (e.env_cycles) { long long d = mw_clock() - t_cta; e.env_cycles[env] = (unsigned)(d > 0xFFFFFFFFll ? 0xFFFFFFFFll : d); }
     w->prof[6] = own - w->prof[7] - (w->prof[0] + w->prof[1] + w->prof[3] + w->prof[4] + w->prof[5]);   // euler + glue
   }
   SYNCW();
@@ -444,13 +448,22 @@ __global__ void k_order_envs(const int* __restrict__ model_first, const int* __r
   //  cost order, i.e. CTAs of similar envs, is what is measured fastest.)
   for (int i = threadIdx.x; i < n; i += blockDim.x) perm[first + i] = (int)(keys[i] & 0xFFFFFFFFull);
 }
-__global__ void k_order_blocks(int n_blocks, const int* __restrict__ block_start, const int* __restrict__ perm, const unsigned* __restrict__ env_cost, int* __restrict__ block_order) {
+// CTAs in order of decreasing predicted duration (the hardware hands CTAs to SMs in launch order as SMs free up: longest
+// first = LPT list scheduling).  Prediction: the longest previous step of the CTA's envs, in cycles of their then-CTAs when
+// `env_cycles` is given (a CTA lasts as long as its slowest warp, whatever the reason: contacts, GJK/EPA, model size),
+// else the solver-work counter of its first env.
+__global__ void k_order_blocks(int n_blocks, const int* __restrict__ block_start, const int* __restrict__ block_count, const int* __restrict__ perm, const unsigned* __restrict__ env_cost,
+                               const unsigned* __restrict__ env_cycles, int* __restrict__ block_order) {
   extern __shared__ unsigned long long keys[];
   if (n_blocks > MW_SORT_MAX) { for (int i = threadIdx.x; i < n_blocks; i += blockDim.x) block_order[i] = i; return; }
   int P = 1; while (P < n_blocks) P <<= 1;
   for (int i = threadIdx.x; i < P; i += blockDim.x) {
     unsigned long long key = ~0ull;
-    if (i < n_blocks) key = ((unsigned long long)(0xFFFFFFFFu - env_cost[perm[block_start[i]]]) << 32) | (unsigned)i;
+    if (i < n_blocks) {
+      unsigned c = env_cost[perm[block_start[i]]];
+      if (env_cycles) { c = 0; for (int j = 0; j < block_count[i]; j++) c = max(c, env_cycles[perm[block_start[i] + j]]); }
+      key = ((unsigned long long)(0xFFFFFFFFu - c) << 32) | (unsigned)i;
+    }
     keys[i] = key;
   }
   bitonic_sort_u64(keys, P);
@@ -466,7 +479,7 @@ struct mw_engine {
   int *d_goal_first = nullptr, *d_goal_count = nullptr, *d_diag = nullptr;
   EpaWs* d_epa = nullptr; WarpSpill* d_spill = nullptr; size_t epa_cap = 0; int slot_by_sm = 0, nsmid = 0;
   unsigned long long* d_prof = nullptr; unsigned long long* d_model_cycles = nullptr; unsigned* d_env_prof = nullptr; int profiling = 0;
-  unsigned* d_env_cost = nullptr; int *d_block_order = nullptr, *d_model_first = nullptr, *d_model_count = nullptr; int n_sorted_models = 0;
+  unsigned* d_env_cost = nullptr; unsigned* d_env_cycles = nullptr; int order_by_cycles = 1, head_warps = 0; int *d_block_order = nullptr, *d_model_first = nullptr, *d_model_count = nullptr; int n_sorted_models = 0;
   std::vector<int> h_faults;                                   // fault bits already drained from d_diag by mw_get_counters
   std::vector<int> env_model; std::vector<int> model_order;   // block table inputs (mw_rebalance re-sorts the models by measured cost)
   // env block table
@@ -475,7 +488,7 @@ struct mw_engine {
   unsigned long long launches = 0, env_steps = 0;
   EngineDev dev() const {
     EngineDev e; e.models = d_models; e.model_stride = model_stride; e.taskconsts = d_tc; e.meshverts = d_meshptrs;
-    e.state = d_state; e.snaps = d_snaps; e.goal_first = d_goal_first; e.goal_count = d_goal_count; e.diag = d_diag; e.epa = d_epa; e.spill = d_spill; e.slot_by_sm = slot_by_sm; e.prof = profiling ? d_prof : nullptr; e.model_cycles = d_model_cycles; e.env_cost = d_env_cost; e.env_prof = profiling ? d_env_prof : nullptr;
+    e.state = d_state; e.snaps = d_snaps; e.goal_first = d_goal_first; e.goal_count = d_goal_count; e.diag = d_diag; e.epa = d_epa; e.spill = d_spill; e.slot_by_sm = slot_by_sm; e.prof = profiling ? d_prof : nullptr; e.model_cycles = d_model_cycles; e.env_cost = d_env_cost; e.env_cycles = order_by_cycles ? d_env_cycles : nullptr; e.env_prof = profiling ? d_env_prof : nullptr;
     e.n_envs = n_envs; e.max_steps = max_steps; e.terminate_on_success = terminate_on_success; e.seed = seed; return e;
   }
 };
@@ -483,15 +496,27 @@ struct mw_engine {
 // group work items by model into CTAs of WARPS_PER_BLOCK warps
 // `order` (optional): models in launch order -- the costliest first, so that the hardware's in-order CTA dispatch behaves
 // like longest-processing-time-first list scheduling and the cheap CTAs fill the tail
+// `head`: size of the FIRST CTA of every model (0 = full; the partial CTA of a model is then its last).  k_order_envs keeps
+// a model's envs sorted by cost, so the first CTA holds its heaviest envs, and with fewer resident warps each of them
+// runs faster (5 warps: ~1.2x per warp).  Measured (MW_B200_HEAD_WARPS, MT50 @ 4096 steady state): 3.42 ms with head 0,
+// 3.46 with the partial CTA first (-1 -> count % WARPS_PER_BLOCK), 3.58 / 3.63 / 3.64 with heads of 4 / 3 / 2 -- the SM
+// that hosts a small CTA is under-used for that CTA's whole life, and in steady state the mean load, not the slowest
+// env, bounds the launch.  Kept as a switch for that measurement only.
 static void make_blocks(int n_models, const std::vector<int>& item_model, std::vector<int>& bm, std::vector<int>& bstart, std::vector<int>& bcount, std::vector<int>& perm,
-                        const std::vector<int>* order = nullptr) {
+                        const std::vector<int>* order = nullptr, int head = 0) {
   bm.clear(); bstart.clear(); bcount.clear(); perm.clear();
   for (int oi = 0; oi < n_models; oi++) {
     const int mi = order && (int)order->size() == n_models ? (*order)[oi] : oi;
     int first = (int)perm.size();
     for (int i = 0; i < (int)item_model.size(); i++) if (item_model[i] == mi) perm.push_back(i);
     int cnt = (int)perm.size() - first;
-    for (int o = 0; o < cnt; o += WARPS_PER_BLOCK) { bm.push_back(mi); bstart.push_back(first + o); bcount.push_back(cnt - o < WARPS_PER_BLOCK ? cnt - o : WARPS_PER_BLOCK); }
+    int h = head < 0 ? cnt % WARPS_PER_BLOCK : head;
+    if (h <= 0 || h > WARPS_PER_BLOCK) h = WARPS_PER_BLOCK;
+    for (int o = 0; o < cnt; ) {
+      const int take = std::min(o == 0 ? h : WARPS_PER_BLOCK, cnt - o);
+      bm.push_back(mi); bstart.push_back(first + o); bcount.push_back(take);
+      o += take;
+    }
   }
 }
 static int ensure_epa(mw_engine* E, size_t n_blocks) {
@@ -526,7 +551,7 @@ template <class T> static int upload(T** dst, const std::vector<T>& v) {
 // (re)builds and uploads the CTA table of the environment set + the buffers of the launch-order kernels
 static int upload_env_blocks(mw_engine* E) {
   std::vector<int> bm, bs, bc, perm;
-  make_blocks(E->n_models, E->env_model, bm, bs, bc, perm, &E->model_order);
+  make_blocks(E->n_models, E->env_model, bm, bs, bc, perm, &E->model_order, E->head_warps);
   E->n_blocks = (int)bm.size();
   if (ensure_epa(E, bm.size())) return MW_ERR_CUDA;
   if (upload(&E->d_block_model, bm) || upload(&E->d_block_start, bs) || upload(&E->d_block_count, bc) || upload(&E->d_perm, perm)) return MW_ERR_CUDA;
@@ -594,6 +619,8 @@ int mw_create(mw_engine** out, int device, int n_models, const void* models, con
   CK(cudaFuncSetAttribute(k_snapshot, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
   CK(cudaFuncSetAttribute(k_substeps, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
   CK(cudaFuncSetAttribute(k_evaluate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
+  { const char* k = getenv("MW_B200_ORDER_KEY"); if (k && !strcmp(k, "work")) E->order_by_cycles = 0; }   // A/B switches of the launch order
+  { const char* k = getenv("MW_B200_HEAD_WARPS"); if (k) E->head_warps = atoi(k); }
   *out = E;
   return MW_OK;
 }
@@ -603,7 +630,7 @@ void mw_destroy(mw_engine* E) {
   cudaSetDevice(E->device);
   cudaFree(E->d_models); cudaFree(E->d_tc); cudaFree(E->d_meshptrs);
   for (float* p : E->meshbufs) cudaFree(p);
-  cudaFree(E->d_state); cudaFree(E->d_snaps); cudaFree(E->d_goal_first); cudaFree(E->d_goal_count); cudaFree(E->d_diag); cudaFree(E->d_epa); cudaFree(E->d_spill); cudaFree(E->d_prof); cudaFree(E->d_model_cycles); cudaFree(E->d_env_prof); cudaFree(E->d_env_cost); cudaFree(E->d_block_order); cudaFree(E->d_model_first); cudaFree(E->d_model_count);
+  cudaFree(E->d_state); cudaFree(E->d_snaps); cudaFree(E->d_goal_first); cudaFree(E->d_goal_count); cudaFree(E->d_diag); cudaFree(E->d_epa); cudaFree(E->d_spill); cudaFree(E->d_prof); cudaFree(E->d_model_cycles); cudaFree(E->d_env_prof); cudaFree(E->d_env_cost); cudaFree(E->d_env_cycles); cudaFree(E->d_block_order); cudaFree(E->d_model_first); cudaFree(E->d_model_count);
   cudaFree(E->d_block_model); cudaFree(E->d_block_start); cudaFree(E->d_block_count); cudaFree(E->d_perm);
   delete E;
 }
@@ -620,6 +647,9 @@ int mw_set_envs(mw_engine* E, int n_envs, const int* env_model) {
   if (E->d_env_cost) cudaFree(E->d_env_cost);
   CK(cudaMalloc((void**)&E->d_env_cost, sizeof(unsigned) * n_envs));
   CK(cudaMemset(E->d_env_cost, 0, sizeof(unsigned) * n_envs));
+  if (E->d_env_cycles) cudaFree(E->d_env_cycles);
+  CK(cudaMalloc((void**)&E->d_env_cycles, sizeof(unsigned) * n_envs));
+  CK(cudaMemset(E->d_env_cycles, 0, sizeof(unsigned) * n_envs));
   if (E->d_state) cudaFree(E->d_state);
   CK(cudaMalloc((void**)&E->d_state, sizeof(MwEnvState) * n_envs));
   CK(cudaMemset(E->d_state, 0, sizeof(MwEnvState) * n_envs));
@@ -703,7 +733,7 @@ int mw_step(mw_engine* E, const float* actions, float* obs, int obs_stride, floa
     int Pm = 1; while (Pm < E->n_envs && Pm < MW_SORT_MAX) Pm <<= 1;
     int Pb = 1; while (Pb < E->n_blocks && Pb < MW_SORT_MAX) Pb <<= 1;
     k_order_envs<<<E->n_sorted_models, 1024, sizeof(unsigned long long) * Pm, (cudaStream_t)stream>>>(E->d_model_first, E->d_model_count, E->d_perm, E->d_env_cost);
-    k_order_blocks<<<1, 1024, sizeof(unsigned long long) * Pb, (cudaStream_t)stream>>>(E->n_blocks, E->d_block_start, E->d_perm, E->d_env_cost, E->d_block_order);
+    k_order_blocks<<<1, 1024, sizeof(unsigned long long) * Pb, (cudaStream_t)stream>>>(E->n_blocks, E->d_block_start, E->d_block_count, E->d_perm, E->d_env_cost, E->order_by_cycles ? E->d_env_cycles : nullptr, E->d_block_order);
   }
   k_step<<<E->n_blocks, BLOCK_THREADS, smem_bytes(), (cudaStream_t)stream>>>(E->dev(), E->d_block_order, E->d_block_model, E->d_block_start, E->d_block_count, E->d_perm,
       actions, obs, obs_stride, reward, terminated, truncated, info, info_stride, final_obs, final_info, next_snapshot);

@@ -171,6 +171,10 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
             ids = torch.tensor([self.env_ids[e % n_types] for e in range(N)], device=dev)
             self.d_obs[torch.arange(N, device=dev), 39 + ids] = 1.0
         self.d_final_obs = self.d_obs.clone()
+        # the numpy API's outputs: the 39 columns k_step writes, packed (stride 39): the constant one-hot columns never cross
+        # the bus, and the host converts a contiguous [N, 39] block
+        self.d_obs39 = torch.zeros(N, 39, device=dev)
+        self.d_final_obs39 = torch.zeros(N, 39, device=dev)
         self.d_reward = torch.zeros(N, device=dev)
         self.d_term = torch.zeros(N, dtype=torch.uint8, device=dev)
         self.d_trunc = torch.zeros(N, dtype=torch.uint8, device=dev)
@@ -187,8 +191,9 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
         self.h_next = pin(torch.zeros(N, dtype=torch.int32))
         self.h_idx = pin(torch.zeros(N, dtype=torch.int64))
         self.h_obs = pin(torch.zeros(N, self.obs_dim))
+        self.h_obs39 = pin(torch.zeros(N, 39))
+        self.h_final_obs39 = pin(torch.zeros(N, 39))
         self.h_small = pin(torch.zeros(N, 9))
-        self.h_final_obs = pin(torch.zeros(N, self.obs_dim))
         self.h_final_info = pin(torch.zeros(N, 8))
         self._next_ids = np.zeros(N, dtype=np.int32)
         self._ep_len = np.zeros(N, dtype=np.int64)
@@ -303,10 +308,10 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
         a = np.ascontiguousarray(actions, dtype=np.float32).reshape(N, 4)
         self.h_actions.copy_(t.from_numpy(a))
         self.d_actions.copy_(self.h_actions, non_blocking=True)
-        self.engine.step(self.d_actions, self.d_obs, self.d_reward, self.d_term, self.d_trunc, self.d_small,
-                         self.d_final_obs, self.d_final_info, self.d_next)
+        self.engine.step(self.d_actions, self.d_obs39, self.d_reward, self.d_term, self.d_trunc, self.d_small,
+                         self.d_final_obs39, self.d_final_info, self.d_next)
         self.h_small.copy_(self.d_small, non_blocking=True)
-        self.h_obs.copy_(self.d_obs, non_blocking=True)
+        self.h_obs39.copy_(self.d_obs39, non_blocking=True)
         # ---- while the kernel runs: everything that does not need its results.
         # Truncations are known in advance (the host mirrors the episode lengths): the terminal rows of those envs are
         # fetched in the same batch of copies, their task streams are advanced and the snapshot ids of the episodes after
@@ -317,7 +322,7 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
             self.h_idx[:npred] = t.from_numpy(pred)
             d_pred = self.d_idx[:npred]
             d_pred.copy_(self.h_idx[:npred], non_blocking=True)
-            self.h_final_obs[:npred].copy_(self.d_final_obs.index_select(0, d_pred), non_blocking=True)
+            self.h_final_obs39[:npred].copy_(self.d_final_obs39.index_select(0, d_pred), non_blocking=True)
             self.h_final_info[:npred].copy_(self.d_final_info.index_select(0, d_pred), non_blocking=True)
             self._advance_streams(pred)
         # fresh arrays every step, like the reference (:637).  The array is allocated here, off the critical path, as a copy
@@ -328,7 +333,7 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
             t.cuda.current_stream(self.device).synchronize()
         # ---- results (single-threaded numpy on purpose: torch's parallel host copies are faster when idle but collapse
         # under a cgroup CPU quota smaller than the machine's core count)
-        np.copyto(obs[:, :39], self.h_obs.numpy()[:, :39])
+        np.copyto(obs[:, :39], self.h_obs39.numpy())
         sm = np.ascontiguousarray(self.h_small.numpy().T, dtype=np.float64)      # [9, N]: rows are contiguous per-key arrays
         reward = sm[7]
         flags = sm[8].astype(np.int8)
@@ -352,12 +357,13 @@ class MetaWorldVecEnv(_gym.VectorEnvBase):
         if any_done:
             # terminal observations / infos of the finished envs only (a few rows per step in steady state)
             if np.array_equal(idx, pred):            # exactly the predicted truncations (always, unless success terminates)
-                rows_o, rows_i = self.h_final_obs[:npred].numpy().copy(), self.h_final_info[:npred].numpy().copy()
+                rows39, rows_i = self.h_final_obs39[:npred].numpy(), self.h_final_info[:npred].numpy().copy()
             else:
                 d_idx = t.from_numpy(idx).to(self.device, non_blocking=True)
-                rows_o = self.d_final_obs.index_select(0, d_idx).cpu().numpy()
+                rows39 = self.d_final_obs39.index_select(0, d_idx).cpu().numpy()
                 rows_i = self.d_final_info.index_select(0, d_idx).cpu().numpy()
-            rows_o = rows_o.astype(self.obs_dtype, copy=False)
+            rows_o = self._obs_template[idx]
+            rows_o[:, :39] = rows39
         if self.post.active:
             if any_done:
                 fo = np.zeros((N, self.obs_dim), dtype=self.obs_dtype)

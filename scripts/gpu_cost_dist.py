@@ -27,6 +27,10 @@ for step in range(1, 401):
         sm_t = np.zeros(148)
         for d in dur:
             i = int(np.argmin(sm_t)); sm_t[i] += d
+        lpt = np.zeros(148)
+        for d in np.sort(dur)[::-1]:
+            i = int(np.argmin(lpt)); lpt[i] += d
+        print(f"   LPT on the true durations would give {lpt.max():.2f} ms")
         print(f"   CTAs {nb}: sum(CTA time)/148 {dur.sum()/148:.2f} ms | greedy makespan {sm_t.max():.2f} ms (SM finish spread {sm_t.min():.2f}..{sm_t.max():.2f}) | "
               f"own work/(148*7) {c.sum()/(148*7)/1965*1e3:.2f} ms | CTA time min/median/max {dur.min():.2f}/{np.median(dur):.2f}/{dur.max():.2f} ms")
         top = np.argsort(-c)[:8]

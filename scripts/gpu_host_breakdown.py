@@ -26,7 +26,7 @@ torch.cuda.synchronize()
 r = np.array(rows) * 1e3
 gpu = np.array([a.elapsed_time(b) for a, b in ev])
 print(f"numpy step {r[:,3].mean():.3f} ms = before sync {r[:,0].mean():.3f} (launch + shadow work) + sync wait {r[:,1].mean():.3f} + after sync {r[:,2].mean():.3f}")
-print(f"GPU busy per step (events around the call, includes copies) {gpu.mean():.3f} ms; host_outputs={env._host_outputs}")
+print(f"GPU busy per step (events around the call, includes copies) {gpu.mean():.3f} ms")
 env.enable_device_sampler()
 a = torch.from_numpy(acts[0]).to(env.device)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -16,6 +16,7 @@ timeout 900 python bench.py --benchmark ML45-train --envs-per-gpu 8192 > gpurun_
 timeout 900 python bench.py --benchmark ML45-test --envs-per-gpu 8192 > gpurun_out/bench_ml45_test.json 2> gpurun_out/bench_ml45_test.err; cut -c1-160 gpurun_out/bench_ml45_test.json
 timeout 600 python scripts/gpu_task_times.py > gpurun_out/task_times.jsonl 2> gpurun_out/task_times.err; echo "task times rc=$?"
 timeout 600 python scripts/gpu_cost_dist.py > gpurun_out/cost_distribution.txt 2>&1; tail -3 gpurun_out/cost_distribution.txt
+timeout 300 python scripts/gpu_host_breakdown.py > gpurun_out/host_breakdown.txt 2>&1; tail -3 gpurun_out/host_breakdown.txt
 MW_BENCH_NCU=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches.csv python bench.py --steps 60 --warmup 5 --e2e-steps 3 --cpu-steps-per-env 5 > gpurun_out/ncu_bench.log 2>&1; echo "ncu list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:k_step -c 1 -f -o gpurun_out/k_step_full python scripts/gpu_ncu_target.py > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"
 ls -la gpurun_out | head -40

@@ -55,6 +55,8 @@ hot = subprocess.run([sys.executable, "scripts/ncu_lines.py", "/tmp/_src.csv", "
 open(os.path.join(P, f"{R}_k_step_hotspots.txt"), "w").write("k_step, MT50 4096 envs, steady state (episode phases uniform over 0..499, scripts/gpu_ncu_target.py; ncu --set full --import-source on; stall samples and executed warp instructions by function / line)\n" + hot)
 if os.path.exists(os.path.join(G, "cost_distribution.txt")):
     open(os.path.join(P, f"{R}_cost_distribution.txt"), "w").write(open(os.path.join(G, "cost_distribution.txt")).read())
+if os.path.exists(os.path.join(G, "host_breakdown.txt")):
+    open(os.path.join(P, f"{R}_host_breakdown.txt"), "w").write("MetaWorldVecEnv.step (numpy API), MT50 @ 4096, steady state; scripts/gpu_host_breakdown.py\n" + open(os.path.join(G, "host_breakdown.txt")).read())
 
 # 4. per-task table
 rows = [json.loads(l) for l in open(os.path.join(G, "task_times.jsonl"))]
