@@ -212,10 +212,8 @@ class MetaWorldSingleEnv:
             # the autoreset inside the terminal step already drew the task the reference's reset() would draw now and
             # started its episode: hand out that observation instead of drawing again
             self._over = False
-            obs = self.vec.d_obs.cpu().numpy().astype(self.vec.obs_dtype)
-            if self.vec.post.active:
-                obs = self.vec.post.on_reset(obs)
-            return obs[0], {}
+            # what the vector step returned for the restarted episode (the optional per-env wrappers already saw this reset)
+            return self._restart_obs[0], {}
         obs, info = self.vec.reset(seed=seed, options=options)
         return obs[0], info
 
@@ -225,6 +223,7 @@ class MetaWorldSingleEnv:
         obs, r, term, trunc, infos = self.vec.step(np.asarray(action, dtype=np.float32)[None])
         if term[0] or trunc[0]:
             self._over = True
+            self._restart_obs = np.array(obs)
             fi = infos["final_info"]
             info = {k: float(fi[k][0]) for k in INFO_KEYS}
             info["episode"] = {k: fi["episode"][k][0] for k in ("r", "l", "t")}

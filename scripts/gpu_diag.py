@@ -87,10 +87,12 @@ def do_reset(task):
 
 def do_open(task):
     g = np.load(os.path.join(GOLD, f"traj_{task}.npz"))
-    rig = Rig(torch, task, g["rand_vec"]); rig.reset()
+    rv = g["rand_vec"].astype(np.float32) if os.environ.get("MW_DIAG_RV32") else g["rand_vec"]     # (float32-rounded goals: the pre-0892805 behaviour)
+    rig = Rig(torch, task, rv); rig.reset()
     for t in range(g["actions"].shape[1]):
         o, r, info, _, _ = rig.step(g["actions"][:, t])
         e = np.abs(o - g["obs"][:, t]).max(axis=1)
+        print(f"   t {t} obs err per env {e} reward err {np.abs(r - g['reward'][:, t])}")
         if (e > 1e-4).any() or not np.isfinite(e).all():
             k = int(np.nanargmax(np.where(np.isfinite(e), e, 1e9)))
             print(f"{task}: open-loop first divergence at step {t} env {k}: {big(o[k], g['obs'][k, t], 1e-4)}")

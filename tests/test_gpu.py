@@ -33,7 +33,10 @@ SENSITIVE_OPEN_LOOP = {"assembly-v3": _JAMMED, "basketball-v3": _TOUCH, "box-clo
                        "disassemble-v3": _JAMMED,
                        "peg-unplug-side-v3": "the plug starts jammed in its socket (SENSITIVE_RESET): the rollout amplifies any change of float32 rounding "
                                              "(e.g. a different FMA contraction after a refactor) to ~3e-4 within 60 steps; single steps agree to 3e-5 (contact-rich test)",
-                       "handle-press-v3": "observations agree to 3e-6; the reward (slope ~50 near the handle) turns that into 1.4e-4"}
+                       "handle-press-v3": "observations agree to 3e-6; the reward (slope ~50 near the handle) turns that into 1.4e-4",
+                       "drawer-close-v3": "goal 0's golden trajectory passes 1.07e-7 m from a contact-activation discontinuity (the left claw grazes the drawer front inside the "
+                                          "1 mm margin at step 2): the float64 oracle itself jumps by 1.08e-4 when the drawer is moved by 1.08e-7 "
+                                          "(tests/test_oracle.py::test_drawer_close_golden_knife_edge); float32 state noise puts the device on the other side"}
 SENSITIVE_ONE_STEP = {"assembly-v3": "the nut rests on the peg (mesh-cylinder contacts under load): single steps reach 1.2e-4"}
 SENSITIVE_CONTACT_RICH = {"soccer-v3": "mesh-mesh face contact (hand against the goal frame): EPA witness point on a flat patch is path dependent"}
 

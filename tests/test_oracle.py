@@ -395,3 +395,32 @@ def test_contact_jacobian_is_the_rate_of_change_of_distance():
                 assert abs((c.dist - d0) / eps - J[row] @ v) < 2e-3 * max(1.0, np.abs(J[row]).sum()), (t, key)
                 checked += 1
     assert checked >= 10
+
+
+def test_drawer_close_golden_knife_edge():
+    """Evidence for the drawer-close entry of tests/test_gpu.py::SENSITIVE_OPEN_LOOP.  Goal 0 of the committed golden rollout
+    sits on a contact discontinuity: at step 2 the left claw (a box) grazes the drawer front (a box with exactly parallel
+    faces) inside the 1 mm margin while moving at ~1 m/s, and which box-box feature pair fires - hence whether the full
+    damping impulse is applied once more - flips back and forth under sub-micrometre displacements of the drawer.  The
+    float64 oracle ITSELF answers displacements of 1e-7 .. 2e-6 m either with a change below 1e-7 or with a jump of
+    1.08e-4 (measured here: +1.0e-7 -> -3e-9, +1.25e-7 -> +1.08e-4, +1.5e-7 -> -5e-9, +1e-6 -> +1.08e-4, +5e-6 -> -2e-7);
+    float32 state noise (ulp 6e-8 at 0.6 m) cannot be expected to stay on the golden side."""
+    from oracle.tasks import TASKS
+    g = np.load(os.path.join(GOLD, "traj_drawer-close-v3.npz"))
+
+    def drawer_y(dy):
+        e = TASKS["drawer-close-v3"]()
+        rv = g["rand_vec"][0][: len(e.random_reset_space()[0])].copy()
+        rv[1] += dy
+        e.set_task_vec(rv, False)
+        e.reset()
+        for t in range(3):
+            o = e.step(g["actions"][0, t])[0]
+        return o[5] - dy
+
+    base = drawer_y(0.0)
+    assert abs(base - g["obs"][0, 2][5]) < 1e-12
+    resp = np.array([abs(drawer_y(d) - base) for d in np.geomspace(2e-8, 3e-6, 40)])
+    assert (resp > 1e-4).sum() >= 3 and (resp < 2e-7).sum() >= 3         # both answers occur, interleaved (a jump already at 2e-8)
+    assert not ((resp > 2e-7) & (resp < 1e-4)).any()                       # and nothing in between: a jump, not a slope
+    assert abs(drawer_y(-1e-6) - base) < 1e-9                              # moving the drawer AWAY from the claw: no effect at all

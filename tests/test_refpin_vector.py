@@ -157,6 +157,32 @@ def test_mt1_single_task_vector_and_explicit_resets(gym):
         assert np.array_equal(renv.unwrapped._last_rand_vec, ours.get_attr("_last_rand_vec")[0])
 
 
+def test_wrapped_single_env_across_truncations(gym):
+    """gym.make("Meta-World/MT1") form (single=True): the TimeLimit step returns the terminal observation, stepping again
+    raises, and reset() starts the task the reference's RandomTaskSelectWrapper draws -- three episodes, with and without
+    the optional per-env wrappers (recurrent observation + exponential reward normalisation)."""
+    import metaworld
+    metaworld._N_GOALS = 5
+    for extra in ({}, dict(recurrent_info_in_obs=True, normalize_reward_in_recurrent_info=True), dict(use_one_hot=False, reward_normalization_method="exponential")):
+        kw = dict(seed=11, max_episode_steps=5, **extra)
+        renv = metaworld.make_mt_envs("drawer-open-v3", **kw)
+        ours = _ours("mt", "drawer-open-v3", num_goals=5, single=True, **kw)
+        o1, _ = renv.reset(); o2, _ = ours.reset()
+        assert o1.shape == o2.shape and np.abs(o1 - o2).max() < 2e-6
+        rng = np.random.default_rng(4)
+        for ep in range(3):
+            for t in range(5):
+                a = rng.uniform(-1, 1, 4).astype(np.float32)
+                x1 = renv.step(a); x2 = ours.step(a)
+                assert np.abs(x1[0] - x2[0]).max() < 2e-6 and abs(x1[1] - x2[1]) < 1e-5, (extra, ep, t)
+                assert bool(x1[2]) == x2[2] and bool(x1[3]) == x2[3] == (t == 4)
+            with pytest.raises(ValueError):
+                ours.step(a)
+            o1, _ = renv.reset(); o2, _ = ours.reset()
+            assert np.abs(o1 - o2).max() < 2e-6, (extra, ep)
+            assert np.array_equal(renv.unwrapped._last_rand_vec, ours._last_rand_vec)
+
+
 def test_bare_single_env_surface_matches_reference_class(gym):
     """`mt1.train_classes[name]()` + set_task / reset / step / evaluate_state and the attributes the reference's own tests
     read (tests/integration/test_new_api.py:18-45, tests/metaworld/envs/mujoco/sawyer_xyz/test_sawyer_xyz_env.py)."""
