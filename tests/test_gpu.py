@@ -283,6 +283,88 @@ def test_full_size_properties(torch_cuda):
     assert np.array_equal(finals[0], finals[1])
 
 
+def _bench_env(benchmark, n):
+    """The exact construction bench.py times (BASELINE configs 2, 3 and 5)."""
+    import sys
+    from types import SimpleNamespace
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+    from bench import build_env
+    return build_env(SimpleNamespace(benchmark=benchmark, envs_per_gpu=n, seed=42), 0, 0)
+
+
+def test_ml45_train_full_size_goal_resampling_reset(torch_cuda):
+    """BASELINE config 5: ML45-train, 8192 envs on one GPU, task_select=pseudorandom, partially observable, goal-resampling
+    reset (metaworld/__init__.py:565-604, wrappers.py:66-123,144-205).  Checked at full size: every reset / autoreset
+    observation is bit-for-bit the float64-build snapshot of the goal the host stream selected (goal columns zeroed), the
+    pseudorandom selector never repeats a goal before the env's own list is exhausted, sample_tasks() re-deals the goals,
+    nothing is dropped, no fault bit is raised."""
+    env, names, _, kind = _bench_env("ML45-train", 8192)
+    N = env.num_envs
+    assert kind == "ml" and N == 8192 and len(names) == 45 and len(set(env.get_attr("task_name"))) == 45
+    env.max_episode_steps = 6; env._set_engine_options()
+    snaps = env.engine.get_snapshots()
+
+    def check_start_obs(obs, rows=None):
+        sid = env.engine.get_state()["snapshot"].astype(np.int64)
+        rows = np.arange(N) if rows is None else rows
+        assert np.array_equal(obs[rows].astype(np.float32), snaps["obs"][sid[rows]])        # the cached double-pass reset, bitwise
+        assert np.all(obs[rows, 36:] == 0) and all(env.get_attr("_partially_observable"))
+        rv = env.get_attr("_last_rand_vec")
+        for e in rows[:: max(1, len(rows) // 64)]:                                             # host stream and device record agree on the goal
+            assert np.array_equal(rv[e], env._task_of_snap[int(sid[e])].unpack()["rand_vec"])
+        return sid
+
+    obs, _ = env.reset()
+    assert obs.shape == (N, 39) and obs.dtype == np.float64
+    seen = [set() for _ in range(N)]
+    sid = check_start_obs(obs)
+    for e in range(N): seen[e].add(int(sid[e]))
+    rng = np.random.default_rng(0)
+    for ep in range(3):
+        for t in range(6):
+            obs, r, term, trunc, infos = env.step(rng.uniform(-1, 1, (N, 4)).astype(np.float32))
+            assert np.isfinite(obs).all() and np.isfinite(r).all() and not term.any() and bool(trunc.all()) == (t == 5)
+            assert np.all(obs[:, 36:] == 0)
+        sid = check_start_obs(obs)                      # SAME_STEP: `obs` is already the next episode's first observation
+        for e in range(N):
+            assert int(sid[e]) not in seen[e]           # pseudorandom: no goal twice before the list (>= 5 goals per env) is exhausted
+            seen[e].add(int(sid[e]))
+    before = env.engine.get_state()["snapshot"].copy()
+    env.call("sample_tasks")                            # the goal-resampling reset of the meta-RL outer loop
+    obs, _ = env.reset()
+    sid = check_start_obs(obs)
+    assert (sid != before).mean() > 0.5
+    c = env.engine.counters()
+    assert c["contacts_dropped"] == 0 and not env.engine.faults().any()
+    env.close()
+
+
+def test_mt10_full_size_one_hot(torch_cuda):
+    """BASELINE config 3: MT10 @ 4096 envs with the one-hot task id (metaworld/env_dict.py:278-291, wrappers.py:17-64): the id
+    columns are exactly the reference's env_id one-hot for every env and survive autoresets, physics columns stay finite
+    and inside the observation space, nothing is dropped."""
+    env, names, n_full, kind = _bench_env("MT10", 4096)
+    N = env.num_envs
+    assert kind == "mt" and len(names) == 10 and n_full == 10
+    env.max_episode_steps = 8; env._set_engine_options()
+    obs, _ = env.reset()
+    assert obs.shape == (N, 49)
+    tn = env.get_attr("task_name")
+    onehot = np.zeros((N, 10)); onehot[np.arange(N), [names.index(n) for n in tn]] = 1
+    lo, hi = env.single_observation_space.low, env.single_observation_space.high
+    rng = np.random.default_rng(1)
+    for t in range(20):
+        obs, r, term, trunc, infos = env.step(rng.uniform(-1, 1, (N, 4)).astype(np.float32))
+        assert np.array_equal(obs[:, 39:], onehot) and np.isfinite(obs).all() and (r >= 0).all() and (r <= 10).all()
+        assert (obs[:, :36] >= lo[:36] - 1e-6).all() and (obs[:, :36] <= hi[:36] + 1e-6).all()
+        assert bool(trunc.all()) == (t % 8 == 7)
+        if trunc.all():
+            fo = np.stack(list(infos["final_obs"]))
+            assert np.array_equal(fo[:, 39:], onehot)
+    assert env.engine.counters()["contacts_dropped"] == 0
+    env.close()
+
+
 def test_evaluation_loop_on_device_envs(torch_cuda):
     """metaworld_b200.evaluation over the real vector env: the reference's `evaluation()` protocol end to end
     (toggle_terminate_on_success, final_info["episode"]["r"], final_info["success"], per-task bookkeeping)."""
