@@ -92,7 +92,10 @@ DEV void stage_model(BlockShared* bs, const unsigned char* src, unsigned bytes, 
 // wires a warp into its CTA's convex-pair queue (mw_physics.cuh: CtaShare); visible to the other warps after the first PHASE_SYNC
 DEV void join_cta(BlockShared* bs, WarpShared* wsa, WarpScratch* w, int warp, int live_warps) {
   if (threadIdx.x == 0) { bs->cs.q_head = 0; bs->cs.nwarp = live_warps; bs->cs.peer_stride = (int)sizeof(WarpShared); bs->cs.peer0 = (unsigned char*)wsa; }
-  if ((threadIdx.x & 31) == 0) { w->cta = &bs->cs; w->warp_in_cta = warp; w->ncand = 0; w->prof_on = 0; }
+  if ((threadIdx.x & 31) == 0) { w->cta = &bs->cs; w->warp_in_cta = warp; w->ncand = 0; w->prof_on = 0; w->nblk1 = mw_tree_split((const MwModel*)bs->model); }
+#ifdef MW_CHOL_ONE_CHAIN     /* A/B switch: never split the factorisation */
+  if ((threadIdx.x & 31) == 0) w->nblk1 = ((const MwModel*)bs->model)->nv;
+#endif
   __syncwarp();
 }
 __device__ void eng_forward(const TaskCtx& c, int lane) { mw_forward(c.m, c.meshvert, c.w, lane); }

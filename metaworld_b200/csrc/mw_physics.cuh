@@ -57,6 +57,7 @@ struct WarpSpill;
 
 struct WarpScratch {
   real lpos[MW_MAXLINK][3], lquat[MW_MAXLINK][4], lmat[MW_MAXLINK][9];
+  real lcom[MW_MAXLINK][3], lIw[MW_MAXLINK][9];   // world COM and world inertia about it (mw_link_inertia; read by mw_mass_matrix, mw_rne_bias)
   real daxis[MW_MAXDOF][3], danchor[MW_MAXDOF][3];
   real qpos[MW_MAXNQ], qvel[MW_MAXDOF], warm[MW_MAXDOF];
   // positions are carried in float64 (state record, kinematic chain, collision inputs): float32 storage of qpos was the
@@ -73,7 +74,8 @@ struct WarpScratch {
   Contact con[MW_SMCON];
   unsigned short cand[MW_MAXCAND];   // this env's general convex candidate pairs of the current pass (pair indices)
   unsigned char achunk[MW_MAXCON];   // 32-pair chunk each analytic contact came from (contact order, see mw_collide)
-  CtaShare* cta; int warp_in_cta, ncand, pad_;
+  CtaShare* cta; int warp_in_cta, ncand;
+  int nblk1;                // mw_tree_split of the model: dofs [0, nblk1) and [nblk1, nv) never share a kinematic tree
   int ncon, nefc, nscalar, nweld, solver_iter, ncon_dropped;
   int fault;                // MW_FAULT_* bits raised by the task code during this step (lane 0)
   int prof_on;              // phase timers enabled (mw_set_profiling)
@@ -202,6 +204,31 @@ DEV void mw_jac_col(const LaneDof& L, unsigned mask, int lane, const real* point
   } else { v3zero(jp); v3zero(jr); }
 }
 
+// World COM and world inertia about the COM (R I R^T) of every link, one link per lane (every lane used to repeat this for
+// every link, once for the mass matrix and once more for the bias forces).
+DEV void mw_link_inertia_one(const MwModel* __restrict__ m, const WarpScratch* w, int l, real* c, real* Iw) {
+  const real* R = w->lmat[l];
+  real cl[3] = {m->link_com[l][0], m->link_com[l][1], m->link_com[l][2]}, t[3];
+  mat_mulvec(t, R, cl); v3add(c, w->lpos[l], t);
+  real I6[6] = {m->link_inertia[l][0], m->link_inertia[l][1], m->link_inertia[l][2], m->link_inertia[l][3], m->link_inertia[l][4], m->link_inertia[l][5]};
+  real Il[9] = {I6[0], I6[3], I6[4], I6[3], I6[1], I6[5], I6[4], I6[5], I6[2]}, T[9];
+  mat_mul(T, R, Il);
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Iw[3 * i + j] = T[3 * i] * R[3 * j] + T[3 * i + 1] * R[3 * j + 1] + T[3 * i + 2] * R[3 * j + 2];
+}
+DEV void mw_link_inertia(const MwModel* __restrict__ m, WarpScratch* w, int lane) {
+#ifdef MW_NO_IW_CACHE
+  return;
+#endif
+  const int l = lane;
+  if (l < m->nlink && m->link_mass[l] > 0) {
+    real c[3], Iw[9];
+    mw_link_inertia_one(m, w, l, c, Iw);
+    for (int i = 0; i < 3; i++) w->lcom[l][i] = c[i];
+    for (int i = 0; i < 9; i++) w->lIw[l][i] = Iw[i];
+  }
+  SYNCW();
+}
+
 // ------------------------------------------------------------------ inertia  [MuJoCo mj_crb]
 // M = sum_links S^T I_link S with spatial vectors about the world origin; lane d owns column d.
 __device__ __noinline__ void mw_mass_matrix(const MwModel* __restrict__ m, WarpScratch* w, const LaneDof& L, int lane) {
@@ -211,18 +238,18 @@ __device__ __noinline__ void mw_mass_matrix(const MwModel* __restrict__ m, WarpS
   real Sa[3], Sl[3];   // spatial motion vector of this lane's dof
   if (L.rot) { v3copy(Sa, L.ax); v3cross(Sl, L.an, L.ax); } else { v3zero(Sa); v3copy(Sl, L.ax); }
   if (!L.valid) { v3zero(Sa); v3zero(Sl); }
+  mw_link_inertia(m, w, lane);
   for (int l = 0; l < m->nlink; l++) {
     real mass = m->link_mass[l];
     if (mass <= 0) continue;
     unsigned mask = m->link_dofmask[l];
-    const real* R = w->lmat[l];
-    real cl[3] = {m->link_com[l][0], m->link_com[l][1], m->link_com[l][2]}, c[3], t[3];
-    mat_mulvec(t, R, cl); v3add(c, w->lpos[l], t);
-    // world inertia about the COM: R I R^T
-    real I6[6] = {m->link_inertia[l][0], m->link_inertia[l][1], m->link_inertia[l][2], m->link_inertia[l][3], m->link_inertia[l][4], m->link_inertia[l][5]};
-    real Il[9] = {I6[0], I6[3], I6[4], I6[3], I6[1], I6[5], I6[4], I6[5], I6[2]}, T[9], Iw[9];
-    mat_mul(T, R, Il);
-    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Iw[3 * i + j] = T[3 * i] * R[3 * j] + T[3 * i + 1] * R[3 * j + 1] + T[3 * i + 2] * R[3 * j + 2];
+    real c[3], t[3], Iw[9];
+#ifndef MW_NO_IW_CACHE
+    for (int i = 0; i < 3; i++) c[i] = w->lcom[l][i];
+    for (int i = 0; i < 9; i++) Iw[i] = w->lIw[l][i];
+#else
+    mw_link_inertia_one(m, w, l, c, Iw);
+#endif
     // momentum of this lane's dof: p = m (v + w x c), Lang = Iw w + c x p
     real pl[3], La[3];
     v3cross(t, Sa, c); for (int i = 0; i < 3; i++) pl[i] = mass * (Sl[i] + t[i]);
@@ -240,50 +267,87 @@ __device__ __noinline__ void mw_mass_matrix(const MwModel* __restrict__ m, WarpS
   SYNCW();
 }
 
-// in-place dense Cholesky of the lower triangle of A (stride NVP); lane i owns row i.  returns min pivot
-// Right-looking with the lane's row held in registers (fully unrolled to MW_MAXDOF, guarded by nv): column j is scaled,
-// broadcast by shuffles and subtracted from the trailing columns.  Every element still receives its updates in increasing
-// column order, so the factor is bit-identical to the left-looking dot-product form this replaces -- at ~40 % of its
-// instruction count (the factorisation runs ~20 times per env step and was 10 % of all issued instructions).
-DEV real mw_chol(real* A, int nv, int lane) {
-  real a[MW_MAXDOF];
+// number of leading dofs that form the kinematic tree of dof 0 (the arm in 46 of the 50 models, the mug's free joint in
+// the coffee models): M is block diagonal over kinematic trees, and so is H = M + J^T D J unless a contact row touches both
+DEV int mw_tree_split(const MwModel* __restrict__ m) {
+  unsigned blk = 0;
+  for (int l = 0; l < m->nlink; l++) if (m->link_dofmask[l] & 1u) blk |= m->link_dofmask[l];
+  const int nb = __ffs(~blk) - 1;                      // length of the run of low set bits
+  return (blk >> nb) != 0 || nb <= 0 ? m->nv : nb;     // the tree's dofs are not a prefix: no split
+}
+
+// in-place Cholesky of the lower triangle of A (stride NVP); lane i owns row i.
+// Right-looking with the lane's row held in registers (fully unrolled to MW_MAXDOF, guarded by the trip count): column j is
+// scaled, broadcast by shuffles and subtracted from the trailing columns; every element receives its updates in increasing
+// column order, so the factor is bit-identical to the left-looking dot-product form.
+// TWO CHAINS: the factorisation is a dependent chain of nv columns (shuffle -> sqrt -> divide -> shuffle -> fma per column)
+// and that latency, not the instruction count, is its cost.  When the block A[nb.., ..nb) is exactly zero (always for M and
+// M + hB, and for H whenever no active contact couples the two trees) the two diagonal blocks are independent problems:
+// lanes < nb factor block 1 while lanes >= nb factor block 2 in the same instruction stream (each lane keeps its row
+// shifted to its block's first column), max(nb, nv - nb) columns instead of nv.  The skipped work is exclusively
+// `x -= l * 0` on the zero block, so the result equals the single-chain factor bit for bit.  One copy of the code
+// (__noinline__; it is 17 KB and used to be inlined at three call sites).  Returns the split that was used (nv: one chain)
+// for mw_chol_solve.
+// (a value the compiler can prove warp-uniform: without it every guarded shuffle is wrapped in divergence handling)
+DEV int mw_uniform(int v, int lane) { return __popc(__ballot_sync(FULLMASK, lane < v)); }
+// columns 0 .. NM-1 of the lane's block.  Columns / rows a block does not have need no guard: no lane has `row >= j` for
+// them, so every update is predicated off (the shuffles are harmless).
+template <int NM> DEV void mw_chol_cols(real* A, int lane, int off, int row, int ncol) {
+  real a[NM];
 #pragma unroll
-  for (int k = 0; k < MW_MAXDOF; k++) a[k] = (lane < nv && k <= lane) ? A[lane * NVP + k] : (real)0;
-  real minpiv = (real)1e30;
+  for (int k = 0; k < NM; k++) a[k] = k <= row ? A[lane * NVP + off + k] : (real)0;
 #pragma unroll
-  for (int j = 0; j < MW_MAXDOF; j++) {
-    if (j < nv) {
-      real piv = bcast(a[j], j);
-      minpiv = fmin(minpiv, piv);
+  for (int j = 0; j < NM; j++) {
+    if (NM <= 10 || j < ncol) {                                  // (uniform; the short variant runs straight through)
+      real piv = __shfl_sync(FULLMASK, a[j], off + j);
       piv = sqrt(fmax(piv, (real)1e-30));
-      const real lij = lane == j ? piv : a[j] / piv;        // L[lane][j] (meaningful for lane >= j)
+      const real lij = row == j ? piv : (row > j ? a[j] / piv : (real)0);    // L[off + row][off + j]
       a[j] = lij;
 #pragma unroll
-      for (int k = j + 1; k < MW_MAXDOF; k++) {
-        if (k < nv) {                                        // (uniform: 20 of the 50 models have nv = 10)
-          const real lkj = bcast(lij, k);                    // L[k][j]
-          if (k <= lane) a[k] -= lij * lkj;
-        }
+      for (int k = j + 1; k < NM; k++) {
+        const real lkj = __shfl_sync(FULLMASK, lij, off + k);  // L[off + k][off + j]
+        if (k <= row) a[k] -= lij * lkj;
       }
     }
   }
 #pragma unroll
-  for (int k = 0; k < MW_MAXDOF; k++) if (lane < nv && k <= lane) A[lane * NVP + k] = a[k];
-  SYNCW();
-  return minpiv;
+  for (int k = 0; k < NM; k++) if (k <= row) A[lane * NVP + off + k] = a[k];
 }
-// solve L L^T x = b ; lane i holds b_i / returns x_i
-DEV real mw_chol_solve(const real* Lm, real b, int nv, int lane) {
-  real y = b;
-  for (int j = 0; j < nv; j++) {
-    real xj = bcast(y, j) / Lm[j * NVP + j];
-    if (lane == j) y = xj;
-    else if (lane > j && lane < nv) y -= Lm[lane * NVP + j] * xj;
+__device__ __noinline__ int mw_chol(real* A, int nv, int nb, int lane) {
+  if (nb < nv) {
+    bool cpl = false;
+    if (lane >= nb && lane < nv) for (int k = 0; k < nb; k++) cpl |= A[lane * NVP + k] != (real)0;
+    if (__any_sync(FULLMASK, cpl)) nb = nv;
   }
-  for (int j = nv - 1; j >= 0; j--) {
-    real xj = bcast(y, j) / Lm[j * NVP + j];
-    if (lane == j) y = xj;
-    else if (lane < j) y -= Lm[j * NVP + lane] * xj;
+  const int off = lane < nb ? 0 : nb;                  // first dof of this lane's block
+  const int row = lane < nv ? lane - off : -1;         // row inside the block (lanes beyond nv hold nothing)
+  const int nmax = mw_uniform(nb > nv - nb ? nb : nv - nb, lane);
+  if (nmax <= 10) mw_chol_cols<10>(A, lane, off, row, nmax);          // every model's blocks have <= 10 dofs
+  else mw_chol_cols<MW_MAXDOF>(A, lane, off, row, nmax);              // one chain (coupled H, or a model without a split)
+  SYNCW();
+  return nb;
+}
+// solve L L^T x = b ; lane i holds b_i / returns x_i.  `nb` is the split mw_chol returned: the substitutions of the two
+// blocks run side by side (2 max(nb, nv - nb) dependent steps instead of 2 nv; same arithmetic per element).
+DEV real mw_chol_solve(const real* Lm, real b, int nv, int nb, int lane) {
+  const int off = lane < nb ? 0 : nb, end = lane < nb ? nb : nv;
+  const int nmax = mw_uniform(nb > nv - nb ? nb : nv - nb, lane);
+  real y = b;
+  for (int j = 0; j < nmax; j++) {
+    const int c = off + j; const bool in = c < end; const int cc = in ? c : 0;
+    real xj = __shfl_sync(FULLMASK, y, cc) / Lm[cc * NVP + cc];
+    if (in) {
+      if (lane == c) y = xj;
+      else if (lane > c && lane < end) y -= Lm[lane * NVP + c] * xj;
+    }
+  }
+  for (int j = nmax - 1; j >= 0; j--) {
+    const int c = off + j; const bool in = c < end; const int cc = in ? c : 0;
+    real xj = __shfl_sync(FULLMASK, y, cc) / Lm[cc * NVP + cc];
+    if (in) {
+      if (lane == c) y = xj;
+      else if (lane < c && lane >= off) y -= Lm[c * NVP + lane] * xj;
+    }
   }
   return lane < nv ? y : (real)0;
 }
@@ -334,13 +398,13 @@ __device__ __noinline__ real mw_rne_bias(const MwModel* __restrict__ m, WarpScra
     real mass = m->link_mass[l];
     real f[6] = {0, 0, 0, 0, 0, 0};
     if (mass > 0) {
-      const real* R = w->lmat[l];
-      real cl[3] = {m->link_com[l][0], m->link_com[l][1], m->link_com[l][2]}, c[3], t[3], u[3];
-      mat_mulvec(t, R, cl); v3add(c, w->lpos[l], t);
-      real I6[6] = {m->link_inertia[l][0], m->link_inertia[l][1], m->link_inertia[l][2], m->link_inertia[l][3], m->link_inertia[l][4], m->link_inertia[l][5]};
-      real Il[9] = {I6[0], I6[3], I6[4], I6[3], I6[1], I6[5], I6[4], I6[5], I6[2]}, T[9], Iw[9];
-      mat_mul(T, R, Il);
-      for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Iw[3 * i + j] = T[3 * i] * R[3 * j] + T[3 * i + 1] * R[3 * j + 1] + T[3 * i + 2] * R[3 * j + 2];
+      real c[3], t[3], u[3], Iw[9];      // from mw_link_inertia (mw_mass_matrix ran on the same poses)
+#ifndef MW_NO_IW_CACHE
+      for (int i = 0; i < 3; i++) c[i] = w->lcom[l][i];
+      for (int i = 0; i < 9; i++) Iw[i] = w->lIw[l][i];
+#else
+      mw_link_inertia_one(m, w, l, c, Iw);
+#endif
       real pl[3], Lm[3], pa[3], La[3];
       v3cross(t, v, c); for (int i = 0; i < 3; i++) pl[i] = mass * (v[3 + i] + t[i]);
       mat_mulvec(Lm, Iw, v); v3cross(t, c, pl); v3add(Lm, Lm, t);
@@ -813,11 +877,14 @@ template <bool SP> DEV void mw_linesearch_eval(const WarpScratch* w, int lane, r
 }
 
 // y_lane = sum_k A[lane][k] x_k  (x published through vTmp)
+// A is the mass matrix: block diagonal over the kinematic trees by construction (mw_mass_matrix only ever touches pairs
+// of dofs of one tree), so a row's sum runs over its own block; the skipped terms are exact zeros times x_k.
 DEV real mw_matvec(const real* A, WarpScratch* w, real x, int nv, int lane) {
   if (lane < nv) w->vTmp[lane] = x;
   SYNCW();
   real s = 0;
-  if (lane < nv) for (int k = 0; k < nv; k++) s += A[lane * NVP + k] * w->vTmp[k];
+  const int nb = w->nblk1, k0 = lane < nb ? 0 : nb, k1 = lane < nb ? nb : nv;
+  if (lane < nv) for (int k = k0; k < k1; k++) s += A[lane * NVP + k] * w->vTmp[k];
   SYNCW();
   return s;
 }
@@ -910,8 +977,8 @@ template <bool SP> __device__ __noinline__ void mw_solve(const MwModel* __restri
       }
     }
     SYNCW();
-    mw_chol(w->H, nv, lane);
-    real search = -mw_chol_solve(w->H, grad, nv, lane);
+    const int nbe = mw_chol(w->H, nv, w->nblk1, lane);
+    real search = -mw_chol_solve(w->H, grad, nv, nbe, lane);
     real Ms = mw_matvec(w->M, w, search, nv, lane);
     if (lane < nv) w->vTmp[lane] = search;
     SYNCW();
@@ -1000,8 +1067,8 @@ __device__ __noinline__ void mw_forward(const MwModel* __restrict__ m, const flo
   // qacc_smooth = M^-1 qfrc_smooth (factor in H)
   for (int i = lane; i < nv * NVP; i += 32) w->H[i] = w->M[i];
   SYNCW();
-  mw_chol(w->H, nv, lane);
-  real as = mw_chol_solve(w->H, qfs, nv, lane);
+  const int nbe = mw_chol(w->H, nv, w->nblk1, lane);
+  real as = mw_chol_solve(w->H, qfs, nv, nbe, lane);
   if (lane < nv) w->qacc_smooth[lane] = as;
   SYNCW();
   PROF_(4, 4)
@@ -1029,9 +1096,9 @@ __device__ __noinline__ void mw_euler(const MwModel* __restrict__ m, WarpScratch
   SYNCW();
   if (lane < nv) w->H[lane * NVP + lane] += h * m->dof_damping[lane];
   SYNCW();
-  mw_chol(w->H, nv, lane);
+  const int nbe = mw_chol(w->H, nv, w->nblk1, lane);
   real rhs = lane < nv ? w->qfrc_smooth[lane] + w->qfrc_con[lane] : (real)0;
-  real acc = mw_chol_solve(w->H, rhs, nv, lane);
+  real acc = mw_chol_solve(w->H, rhs, nv, nbe, lane);
   if (lane < nv) { w->qvel[lane] += h * acc; w->warm[lane] = w->qacc[lane]; }
   SYNCW();
   // positions (float64 state; the float copy is refreshed for the dynamics)

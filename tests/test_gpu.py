@@ -302,6 +302,10 @@ def test_ml45_train_full_size_goal_resampling_reset(torch_cuda):
     N = env.num_envs
     assert kind == "ml" and N == 8192 and len(names) == 45 and len(set(env.get_attr("task_name"))) == 45
     env.max_episode_steps = 6; env._set_engine_options()
+    # the pseudorandom selector only re-deals on reset when asked to (wrappers.py:144-205: sample_tasks_on_reset defaults to
+    # False for it, the meta-RL outer loop calls sample_tasks()); the goal-randomised reset of config 5 switches it on
+    assert not any(env.get_attr("sample_tasks_on_reset"))
+    env.call("toggle_sample_tasks_on_reset", True)
     snaps = env.engine.get_snapshots()
 
     def check_start_obs(obs, rows=None):
