@@ -109,9 +109,10 @@ DEV long long mw_clock() { long long t; asm volatile("mov.u64 %0, %%clock64;" : 
 // Sequential over the (short) link chain; every lane computes the same values, lane 0 stores.
 __device__ __noinline__ void mw_kinematics(const MwModel* __restrict__ m, WarpScratch* w, int lane) {
   const int nl = m->nlink;
+  double quat[4], R[9];          // orientation of the link in work; at the top of an iteration: of the previous link
   for (int l = 0; l < nl; l++) {
     int p = m->link_parent[l];
-    double pos[3], quat[4], R[9];
+    double pos[3];
     if (p < 0) {
       if (m->link_shift[l]) { for (int i = 0; i < 3; i++) pos[i] = (double)m->link_pos[l][i] + (double)w->shift[i]; }
       else { for (int i = 0; i < 3; i++) pos[i] = m->link_pos[l][i]; }
@@ -119,16 +120,21 @@ __device__ __noinline__ void mw_kinematics(const MwModel* __restrict__ m, WarpSc
     } else {
       double lp[3] = {m->link_pos[l][0], m->link_pos[l][1], m->link_pos[l][2]};
       double lq[4] = {m->link_quat[l][0], m->link_quat[l][1], m->link_quat[l][2], m->link_quat[l][3]};
-      double Rp[9], t[3]; quat2mat(Rp, w->lquatd[p]); mat_mulvec(t, Rp, lp); v3add(pos, w->lposd[p], t);
-      quat_mul(quat, w->lquatd[p], lq);
+      // the arm is a chain: the parent is usually the previous link, whose matrix and quaternion are still in registers
+      double Rp[9], pq[4], t[3];
+      if (p == l - 1) { for (int i = 0; i < 9; i++) Rp[i] = R[i]; for (int i = 0; i < 4; i++) pq[i] = quat[i]; }
+      else { for (int i = 0; i < 4; i++) pq[i] = w->lquatd[p][i]; quat2mat(Rp, pq); }
+      mat_mulvec(t, Rp, lp); v3add(pos, w->lposd[p], t);
+      quat_mul(quat, pq, lq);
     }
     const int jt = m->link_jtype[l], qa = m->link_qadr[l], da = m->link_dadr[l];
+    bool fresh = false;          // `quat` has just been normalised and R is its matrix
     if (jt == JT_FREE) {
       double q[4] = {w->qposd[qa + 3], w->qposd[qa + 4], w->qposd[qa + 5], w->qposd[qa + 6]};
       quat_normalize(q);
       for (int i = 0; i < 3; i++) pos[i] = w->qposd[qa + i];
       for (int i = 0; i < 4; i++) quat[i] = q[i];
-      quat2mat(R, quat);
+      quat2mat(R, quat); fresh = true;
       if (lane == 0) {
         for (int i = 0; i < 4; i++) QSET(w, qa + 3 + i, q[i]);
         for (int i = 0; i < 3; i++) {
@@ -141,7 +147,8 @@ __device__ __noinline__ void mw_kinematics(const MwModel* __restrict__ m, WarpSc
       double jax[3] = {m->link_jaxis[l][0], m->link_jaxis[l][1], m->link_jaxis[l][2]};
       double jp[3] = {m->link_jpos[l][0], m->link_jpos[l][1], m->link_jpos[l][2]};
       double axis[3], anchor[3], t[3];
-      quat_normalize(quat);
+      // joint axis and anchor in the frame the body has before its own joint moves it (a product of unit quaternions:
+      // like mj_kinematics, no normalisation before the end of the body)
       quat2mat(R, quat);
       mat_mulvec(axis, R, jax);
       mat_mulvec(t, R, jp); v3add(anchor, pos, t);
@@ -153,13 +160,12 @@ __device__ __noinline__ void mw_kinematics(const MwModel* __restrict__ m, WarpSc
         quat_mul(qn, quat, qr);
         for (int i = 0; i < 4; i++) quat[i] = qn[i];
         quat_normalize(quat);
-        quat2mat(R, quat);
+        quat2mat(R, quat); fresh = true;
         mat_mulvec(t, R, jp); v3sub(pos, anchor, t);
       }
       if (lane == 0) for (int k = 0; k < 3; k++) { w->daxis[da][k] = (real)axis[k]; w->danchor[da][k] = (real)anchor[k]; }
     }
-    quat_normalize(quat);
-    quat2mat(R, quat);
+    if (!fresh) { quat_normalize(quat); quat2mat(R, quat); }
     if (lane == 0) {
       for (int i = 0; i < 3; i++) { w->lposd[l][i] = pos[i]; w->lpos[l][i] = (real)pos[i]; }
       for (int i = 0; i < 4; i++) { w->lquatd[l][i] = quat[i]; w->lquat[l][i] = (real)quat[i]; }
@@ -216,9 +222,6 @@ DEV void mw_link_inertia_one(const MwModel* __restrict__ m, const WarpScratch* w
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Iw[3 * i + j] = T[3 * i] * R[3 * j] + T[3 * i + 1] * R[3 * j + 1] + T[3 * i + 2] * R[3 * j + 2];
 }
 DEV void mw_link_inertia(const MwModel* __restrict__ m, WarpScratch* w, int lane) {
-#ifdef MW_NO_IW_CACHE
-  return;
-#endif
   const int l = lane;
   if (l < m->nlink && m->link_mass[l] > 0) {
     real c[3], Iw[9];
@@ -244,12 +247,8 @@ __device__ __noinline__ void mw_mass_matrix(const MwModel* __restrict__ m, WarpS
     if (mass <= 0) continue;
     unsigned mask = m->link_dofmask[l];
     real c[3], t[3], Iw[9];
-#ifndef MW_NO_IW_CACHE
     for (int i = 0; i < 3; i++) c[i] = w->lcom[l][i];
     for (int i = 0; i < 9; i++) Iw[i] = w->lIw[l][i];
-#else
-    mw_link_inertia_one(m, w, l, c, Iw);
-#endif
     // momentum of this lane's dof: p = m (v + w x c), Lang = Iw w + c x p
     real pl[3], La[3];
     v3cross(t, Sa, c); for (int i = 0; i < 3; i++) pl[i] = mass * (Sl[i] + t[i]);
@@ -288,6 +287,9 @@ DEV int mw_tree_split(const MwModel* __restrict__ m) {
 // `x -= l * 0` on the zero block, so the result equals the single-chain factor bit for bit.  One copy of the code
 // (__noinline__; it is 17 KB and used to be inlined at three call sites).  Returns the split that was used (nv: one chain)
 // for mw_chol_solve.
+// x / d for d > 0 without the division's slow path when x is exactly zero (right-hand sides are full of exact zeros: a
+// resting object's dofs); the result is the same zero
+DEV real mw_div_nz(real x, real d) { const real q = (x != (real)0 ? x : (real)1) / d; return x != (real)0 ? q : x; }
 // (a value the compiler can prove warp-uniform: without it every guarded shuffle is wrapped in divergence handling)
 DEV int mw_uniform(int v, int lane) { return __popc(__ballot_sync(FULLMASK, lane < v)); }
 // columns 0 .. NM-1 of the lane's block.  Columns / rows a block does not have need no guard: no lane has `row >= j` for
@@ -301,7 +303,13 @@ template <int NM> DEV void mw_chol_cols(real* A, int lane, int off, int row, int
     if (NM <= 10 || j < ncol) {                                  // (uniform; the short variant runs straight through)
       real piv = __shfl_sync(FULLMASK, a[j], off + j);
       piv = sqrt(fmax(piv, (real)1e-30));
-      const real lij = row == j ? piv : (row > j ? a[j] / piv : (real)0);    // L[off + row][off + j]
+      // (a zero numerator sends the IEEE division to its slow path -- a 30-instruction subroutine on the factorisation's
+      // critical chain -- and most lanes hold one: rows above the pivot, structural zeros of the block.  0 / piv = 0 with
+      // the sign of the zero, so those lanes divide 1 instead and keep their zero)
+      const real aj = a[j];
+      const bool dv = row > j && aj != (real)0;
+      const real qt = (dv ? aj : (real)1) / piv;
+      const real lij = row == j ? piv : (dv ? qt : (row > j ? aj : (real)0));  // L[off + row][off + j]
       a[j] = lij;
 #pragma unroll
       for (int k = j + 1; k < NM; k++) {
@@ -329,13 +337,15 @@ __device__ __noinline__ int mw_chol(real* A, int nv, int nb, int lane) {
 }
 // solve L L^T x = b ; lane i holds b_i / returns x_i.  `nb` is the split mw_chol returned: the substitutions of the two
 // blocks run side by side (2 max(nb, nv - nb) dependent steps instead of 2 nv; same arithmetic per element).
+// (A fully unrolled variant with the lane's row and column of L in registers, the counterpart of mw_chol_cols, was measured
+// 2.6 % SLOWER per env step on B200 -- identical results -- and is not used.)
 DEV real mw_chol_solve(const real* Lm, real b, int nv, int nb, int lane) {
   const int off = lane < nb ? 0 : nb, end = lane < nb ? nb : nv;
   const int nmax = mw_uniform(nb > nv - nb ? nb : nv - nb, lane);
   real y = b;
   for (int j = 0; j < nmax; j++) {
     const int c = off + j; const bool in = c < end; const int cc = in ? c : 0;
-    real xj = __shfl_sync(FULLMASK, y, cc) / Lm[cc * NVP + cc];
+    real xj = mw_div_nz(__shfl_sync(FULLMASK, y, cc), Lm[cc * NVP + cc]);
     if (in) {
       if (lane == c) y = xj;
       else if (lane > c && lane < end) y -= Lm[lane * NVP + c] * xj;
@@ -343,7 +353,7 @@ DEV real mw_chol_solve(const real* Lm, real b, int nv, int nb, int lane) {
   }
   for (int j = nmax - 1; j >= 0; j--) {
     const int c = off + j; const bool in = c < end; const int cc = in ? c : 0;
-    real xj = __shfl_sync(FULLMASK, y, cc) / Lm[cc * NVP + cc];
+    real xj = mw_div_nz(__shfl_sync(FULLMASK, y, cc), Lm[cc * NVP + cc]);
     if (in) {
       if (lane == c) y = xj;
       else if (lane < c && lane >= off) y -= Lm[c * NVP + lane] * xj;
@@ -399,12 +409,8 @@ __device__ __noinline__ real mw_rne_bias(const MwModel* __restrict__ m, WarpScra
     real f[6] = {0, 0, 0, 0, 0, 0};
     if (mass > 0) {
       real c[3], t[3], u[3], Iw[9];      // from mw_link_inertia (mw_mass_matrix ran on the same poses)
-#ifndef MW_NO_IW_CACHE
       for (int i = 0; i < 3; i++) c[i] = w->lcom[l][i];
       for (int i = 0; i < 9; i++) Iw[i] = w->lIw[l][i];
-#else
-      mw_link_inertia_one(m, w, l, c, Iw);
-#endif
       real pl[3], Lm[3], pa[3], La[3];
       v3cross(t, v, c); for (int i = 0; i < 3; i++) pl[i] = mass * (v[3 + i] + t[i]);
       mat_mulvec(Lm, Iw, v); v3cross(t, c, pl); v3add(Lm, Lm, t);
@@ -418,7 +424,8 @@ __device__ __noinline__ real mw_rne_bias(const MwModel* __restrict__ m, WarpScra
     if (lane == 0) for (int c = 0; c < 6; c++) { cvel[6 * l + c] = v[c]; cacc[6 * l + c] = a[c]; cfrc[6 * l + c] = f[c]; }
     SYNCW();
   }
-  if (lane == 0) for (int l = nl - 1; l >= 0; l--) { int p = m->link_parent[l]; if (p >= 0) for (int c = 0; c < 6; c++) cfrc[6 * p + c] += cfrc[6 * l + c]; }
+  // leaves-to-root accumulation of the link forces: the six components are independent, one lane each
+  if (lane < 6) for (int l = nl - 1; l >= 0; l--) { int p = m->link_parent[l]; if (p >= 0) cfrc[6 * p + lane] += cfrc[6 * l + lane]; }
   SYNCW();
   real bias = 0;
   if (L.valid) {
@@ -940,14 +947,22 @@ template <bool SP> __device__ __noinline__ void mw_solve(const MwModel* __restri
     if (lane < nv) { grad = Ma - qfs; for (int r = 0; r < nefc; r++) grad -= JROW(r)[lane] * EV(eF, r); }
     real gn = sqrt(warp_sum(grad * grad));
     if (scale * gn < tol) break;
-    // H = M + J^T Hblocks J : lane b owns column b, lower triangle a >= b
-    if (lane < nv) {
-      for (int a = lane; a < nv; a++) w->H[a * NVP + lane] = w->M[a * NVP + lane];
+    // H = M + J^T Hblocks J : lane b owns column b, lower triangle a >= b.  The column is accumulated in registers (fully
+    // unrolled over the rows with guards, the Jacobian entries arrive as shared-memory broadcasts) and stored once; every
+    // element receives its terms in the same order as a read-modify-write loop over shared memory would give it.
+    {
+      real h[MW_MAXDOF];
+      const bool own = lane < nv;
+#pragma unroll
+      for (int a = 0; a < MW_MAXDOF; a++) h[a] = (own && a >= lane && a < nv) ? w->M[a * NVP + lane] : (real)0;
       for (int r = 0; r < w->nscalar; r++) {
-        real hd = w->eHd[r];
+        const real hd = w->eHd[r];
         if (hd == 0) continue;
-        real wb = hd * JROW(r)[lane];
-        if (wb != 0) for (int a = lane; a < nv; a++) w->H[a * NVP + lane] += JROW(r)[a] * wb;
+        const real* Jr = JROW(r);
+        const real wb = own ? hd * Jr[lane] : (real)0;
+        const bool on = wb != 0;
+#pragma unroll
+        for (int a = 0; a < MW_MAXDOF; a++) if (a < nv) { const real ja = Jr[a]; if (on && a >= lane) h[a] += ja * wb; }
       }
       for (int c = 0; c < w->ncon; c++) {
         const Contact* con = CON(c);
@@ -956,10 +971,11 @@ template <bool SP> __device__ __noinline__ void mw_solve(const MwModel* __restri
         // dofs that can move either body: every other column of these rows is exactly zero, so skipping them adds nothing
         const int cl1 = m->geom_link[con->g1], cl2 = m->geom_link[con->g2];
         const unsigned cmask = (cl1 < 0 ? 0u : m->link_dofmask[cl1]) | (cl2 < 0 ? 0u : m->link_dofmask[cl2]);
-        if (!((cmask >> lane) & 1u)) continue;
+        const bool on = own && ((cmask >> lane) & 1u);
         real Jb[4] = {0, 0, 0, 0}, t[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) if (k < dim) Jb[k] = JROW(r0 + k)[lane];
+        const real* J0 = JROW(r0); const real* J1 = JROW(r0 + 1); const real* J2 = JROW(r0 + 2); const real* J3 = JROW(r0 + 3);
+        const int ln = own ? lane : 0;
+        Jb[0] = J0[ln]; if (dim > 1) Jb[1] = J1[ln]; if (dim > 2) Jb[2] = J2[ln]; if (dim > 3) Jb[3] = J3[ln];
         // t = Hc * Jb (packed symmetric upper, row-major 4x4; entries beyond dim are zero)
         const real* Hc = con->H;
         const real h0 = Hc[0], h1 = Hc[1], h2 = Hc[2], h3 = Hc[3], h4 = Hc[4], h5 = Hc[5], h6 = Hc[6], h7 = Hc[7], h8 = Hc[8], h9 = Hc[9];
@@ -967,14 +983,19 @@ template <bool SP> __device__ __noinline__ void mw_solve(const MwModel* __restri
         t[1] = h1 * Jb[0] + h4 * Jb[1] + h5 * Jb[2] + h6 * Jb[3];
         t[2] = h2 * Jb[0] + h5 * Jb[1] + h7 * Jb[2] + h8 * Jb[3];
         t[3] = h3 * Jb[0] + h6 * Jb[1] + h8 * Jb[2] + h9 * Jb[3];
-        for (unsigned rem = cmask >> lane << lane; rem; rem &= rem - 1) {
-          const int a = __ffs(rem) - 1;
-          real s = 0;
 #pragma unroll
-          for (int k = 0; k < 4; k++) if (k < dim) s += JROW(r0 + k)[a] * t[k];
-          w->H[a * NVP + lane] += s;
+        for (int a = 0; a < MW_MAXDOF; a++) {
+          if ((cmask >> a) & 1u) {                       // (uniform: the contact is the same for every lane)
+            real s = J0[a] * t[0];
+            if (dim > 1) s += J1[a] * t[1];
+            if (dim > 2) s += J2[a] * t[2];
+            if (dim > 3) s += J3[a] * t[3];
+            if (on && a >= lane) h[a] += s;
+          }
         }
       }
+#pragma unroll
+      for (int a = 0; a < MW_MAXDOF; a++) if (own && a >= lane && a < nv) w->H[a * NVP + lane] = h[a];
     }
     SYNCW();
     const int nbe = mw_chol(w->H, nv, w->nblk1, lane);
