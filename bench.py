@@ -292,11 +292,19 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if os.environ.get("MW_BENCH_SWAP") == "1" and world == 2:       # diagnosis: rank r on device 1 - r
+        local = 1 - local
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if os.environ.get("MW_BENCH_PG", "nccl") == "gloo":      # diagnosis only (scripts/gpu_2gpu_diag.sh)
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from metaworld_b200.engine import lib
 
+    seed_rank = int(os.environ.get("MW_BENCH_FAKE_RANK", rank))     # diagnosis: a single process with rank r's random streams
+    if seed_rank != rank:
+        rank_true, rank = rank, seed_rank
     env, names, n_full, kind = build_env(args, rank, local)
     N = args.envs_per_gpu
     dev = env.device
@@ -404,7 +412,13 @@ def run_ours(args):
     prof = env.engine.profile()
     env.engine.set_profiling(False)
     t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+    if world > 1 or "MW_BENCH_FAKE_RANK" in os.environ:
+        sys.stderr.write(f"[bench] rank {rank} on cuda:{local}: {ms / K:.4f} ms per step (device), e2e {e2e_s * 1e3 / Ke:.4f} ms, "
+                         f"own work {(prof['step'] - prof['barrier_wait']) / max(1, N * min(K, 20)):.0f} cycles per env step, "
+                         f"convex pairs {prof['n_convex_pairs'] / max(1, N * min(K, 20)):.3f}\n")
     if world > 1:
+        if dist.get_backend() == "gloo":
+            t = t.cpu()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(t[0]), float(t[1])
     if rank == 0:

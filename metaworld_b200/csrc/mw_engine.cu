@@ -153,11 +153,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 1)
 k_step(EngineDev e, const int* __restrict__ block_order, const int* __restrict__ block_model, const int* __restrict__ block_start, const int* __restrict__ block_count,
        const int* __restrict__ perm, const float* __restrict__ actions, float* __restrict__ obs_out, int obs_stride,
        float* __restrict__ reward, unsigned char* __restrict__ terminated, unsigned char* __restrict__ truncated,
-       float* __restrict__ info_out, int info_stride, float* __restrict__ final_obs, float* __restrict__ final_info, const int* __restrict__ next_snapshot) {
+       float* __restrict__ info_out, int info_stride, float* __restrict__ final_obs, float* __restrict__ final_info, const int* __restrict__ next_snapshot,
+       const int* __restrict__ block_live) {
   extern __shared__ __align__(16) unsigned char smem[];
   BlockShared* bs = (BlockShared*)smem;
   WarpShared* wsa = (WarpShared*)(smem + sizeof(BlockShared));
   const int blk = block_order[blockIdx.x];             // launch slot -> CTA work item (costliest first, see k_order_*)
+  if (block_live && !block_live[blk]) return;          // the other decomposition of this model's head is running (k_order_blocks)
   const int mi = block_model[blk];
   stage_model(bs, e.models + (size_t)mi * e.model_stride, (unsigned)sizeof(bs->model), e.taskconsts + mi);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -455,16 +457,54 @@ __global__ void k_order_envs(const int* __restrict__ model_first, const int* __r
 // first = LPT list scheduling).  Prediction: the longest previous step of the CTA's envs, in cycles of their then-CTAs when
 // `env_cycles` is given (a CTA lasts as long as its slowest warp, whatever the reason: contacts, GJK/EPA, model size),
 // else the solver-work counter of its first env.
+// HEAD SPLIT (opt in, MW_B200_SPLIT_FRAC): k_order_envs keeps a model's envs sorted by cost, so the first CTA of a model holds
+// its seven heaviest envs; when those are pathological (a jammed plug, a lid wedged on its box: 5-6 M cycles each against a
+// mean of 1.1 M) that one CTA outlasts the balanced load of an SM and IS the duration of the launch.  Fewer resident warps
+// run faster each (4 warps: ~1.3 x per warp), so every such model also owns two alternative CTAs that cover the same seven
+// envs with `split` and 7 - `split` warps; per step exactly one of {head} / {alt 1, alt 2} is live.  A head is split while its
+// predicted duration exceeds `frac` x (sum of the predicted CTA durations / number of SMs), with hysteresis (a split head's
+// envs report shorter residences).  Dead CTAs sort last and exit at once.  Pure scheduling: results do not depend on it.
 __global__ void k_order_blocks(int n_blocks, const int* __restrict__ block_start, const int* __restrict__ block_count, const int* __restrict__ perm, const unsigned* __restrict__ env_cost,
-                               const unsigned* __restrict__ env_cycles, int* __restrict__ block_order) {
+                               const unsigned* __restrict__ env_cycles, int* __restrict__ block_order,
+                               int n_base, int n_split, const int* __restrict__ split_head, const int* __restrict__ split_alt, int* __restrict__ split_state,
+                               int* __restrict__ block_live, float frac, int n_sm) {
   extern __shared__ unsigned long long keys[];
-  if (n_blocks > MW_SORT_MAX) { for (int i = threadIdx.x; i < n_blocks; i += blockDim.x) block_order[i] = i; return; }
+  __shared__ unsigned long long total;
+  if (n_blocks > MW_SORT_MAX) {
+    for (int i = threadIdx.x; i < n_blocks; i += blockDim.x) { block_order[i] = i; if (block_live) block_live[i] = i < n_base; }
+    return;
+  }
+  auto predicted = [&](int i) -> unsigned {
+    unsigned c = env_cost[perm[block_start[i]]];
+    if (env_cycles) { c = 0; for (int j = 0; j < block_count[i]; j++) c = max(c, env_cycles[perm[block_start[i] + j]]); }
+    return c;
+  };
+  if (block_live) {
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    unsigned long long part = 0;
+    for (int i = threadIdx.x; i < n_base; i += blockDim.x) part += predicted(i);
+    if (part) atomicAdd(&total, part);
+    for (int i = threadIdx.x; i < n_blocks; i += blockDim.x) block_live[i] = i < n_base;
+    __syncthreads();
+    const float hi = frac * (float)total / (float)(n_sm > 0 ? n_sm : 1), lo = 0.7f * hi;
+    for (int s = threadIdx.x; s < n_split; s += blockDim.x) {
+      const int h = split_head[s], a1 = split_alt[s];
+      const float c = (float)predicted(h);
+      int st = split_state[s];
+      if (!env_cycles || frac <= 0) st = 0;
+      else if (!st && c > hi && hi > 0) st = 1;
+      else if (st && c < lo) st = 0;
+      split_state[s] = st;
+      block_live[h] = !st; block_live[a1] = st; block_live[a1 + 1] = st;
+    }
+    __syncthreads();
+  }
   int P = 1; while (P < n_blocks) P <<= 1;
   for (int i = threadIdx.x; i < P; i += blockDim.x) {
     unsigned long long key = ~0ull;
     if (i < n_blocks) {
-      unsigned c = env_cost[perm[block_start[i]]];
-      if (env_cycles) { c = 0; for (int j = 0; j < block_count[i]; j++) c = max(c, env_cycles[perm[block_start[i] + j]]); }
+      const unsigned c = (block_live && !block_live[i]) ? 0u : predicted(i);
       key = ((unsigned long long)(0xFFFFFFFFu - c) << 32) | (unsigned)i;
     }
     keys[i] = key;
@@ -487,6 +527,9 @@ struct mw_engine {
   std::vector<int> env_model; std::vector<int> model_order;   // block table inputs (mw_rebalance re-sorts the models by measured cost)
   // env block table
   int n_blocks = 0; int *d_block_model = nullptr, *d_block_start = nullptr, *d_block_count = nullptr, *d_perm = nullptr;
+  // head split (k_order_blocks): the alternative CTAs follow the n_blocks regular ones in the block table
+  int n_blocks_total = 0, n_split = 0, split_warps = 4, n_sm = 0; float split_frac = 0.f;
+  int *d_split_head = nullptr, *d_split_alt = nullptr, *d_split_state = nullptr, *d_block_live = nullptr;
   int max_steps = 500, terminate_on_success = 0; unsigned long long seed = 0;
   unsigned long long launches = 0, env_steps = 0;
   EngineDev dev() const {
@@ -556,16 +599,32 @@ static int upload_env_blocks(mw_engine* E) {
   std::vector<int> bm, bs, bc, perm;
   make_blocks(E->n_models, E->env_model, bm, bs, bc, perm, &E->model_order, E->head_warps);
   E->n_blocks = (int)bm.size();
-  if (ensure_epa(E, bm.size())) return MW_ERR_CUDA;
-  if (upload(&E->d_block_model, bm) || upload(&E->d_block_start, bs) || upload(&E->d_block_count, bc) || upload(&E->d_perm, perm)) return MW_ERR_CUDA;
-  std::vector<int> mfirst, mcount, order(bm.size());
+  std::vector<int> mfirst, mcount;
   for (size_t b = 0; b < bm.size(); b++) {
-    order[b] = (int)b;
     if (b == 0 || bm[b] != bm[b - 1]) { mfirst.push_back(bs[b]); mcount.push_back(0); }
     mcount.back() += bc[b];
   }
+  // alternative decomposition of every full first CTA of a model (head split, see k_order_blocks)
+  std::vector<int> shead, salt;
+  const int sw = E->split_warps;
+  if (E->split_frac > 0 && sw > 0 && sw < WARPS_PER_BLOCK) {
+    const size_t nb = bm.size();
+    for (size_t b = 0; b < nb; b++) {
+      if ((b == 0 || bm[b] != bm[b - 1]) && bc[b] == WARPS_PER_BLOCK) {
+        shead.push_back((int)b); salt.push_back((int)bm.size());
+        bm.push_back(bm[b]); bs.push_back(bs[b]); bc.push_back(sw);
+        bm.push_back(bm[b]); bs.push_back(bs[b] + sw); bc.push_back(WARPS_PER_BLOCK - sw);
+      }
+    }
+  }
+  E->n_split = (int)shead.size(); E->n_blocks_total = (int)bm.size();
+  if (ensure_epa(E, bm.size())) return MW_ERR_CUDA;
+  if (upload(&E->d_block_model, bm) || upload(&E->d_block_start, bs) || upload(&E->d_block_count, bc) || upload(&E->d_perm, perm)) return MW_ERR_CUDA;
+  std::vector<int> order(bm.size()), live(bm.size()), zero(shead.size() ? shead.size() : 1, 0);
+  for (size_t b = 0; b < bm.size(); b++) { order[b] = (int)b; live[b] = b < (size_t)E->n_blocks; }
   E->n_sorted_models = (int)mfirst.size();
   if (upload(&E->d_model_first, mfirst) || upload(&E->d_model_count, mcount) || upload(&E->d_block_order, order)) return MW_ERR_CUDA;
+  if (upload(&E->d_split_head, shead) || upload(&E->d_split_alt, salt) || upload(&E->d_split_state, zero) || upload(&E->d_block_live, live)) return MW_ERR_CUDA;
   return 0;
 }
 
@@ -624,6 +683,9 @@ int mw_create(mw_engine** out, int device, int n_models, const void* models, con
   CK(cudaFuncSetAttribute(k_evaluate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes()));
   { const char* k = getenv("MW_B200_ORDER_KEY"); if (k && !strcmp(k, "work")) E->order_by_cycles = 0; }   // A/B switches of the launch order
   { const char* k = getenv("MW_B200_HEAD_WARPS"); if (k) E->head_warps = atoi(k); }
+  { const char* k = getenv("MW_B200_SPLIT_FRAC"); if (k) E->split_frac = (float)atof(k); }
+  { const char* k = getenv("MW_B200_SPLIT_WARPS"); if (k) E->split_warps = atoi(k); }
+  { cudaDeviceProp pr; CK(cudaGetDeviceProperties(&pr, device)); E->n_sm = pr.multiProcessorCount; }
   *out = E;
   return MW_OK;
 }
@@ -635,6 +697,7 @@ void mw_destroy(mw_engine* E) {
   for (float* p : E->meshbufs) cudaFree(p);
   cudaFree(E->d_state); cudaFree(E->d_snaps); cudaFree(E->d_goal_first); cudaFree(E->d_goal_count); cudaFree(E->d_diag); cudaFree(E->d_epa); cudaFree(E->d_spill); cudaFree(E->d_prof); cudaFree(E->d_model_cycles); cudaFree(E->d_env_prof); cudaFree(E->d_env_cost); cudaFree(E->d_env_cycles); cudaFree(E->d_block_order); cudaFree(E->d_model_first); cudaFree(E->d_model_count);
   cudaFree(E->d_block_model); cudaFree(E->d_block_start); cudaFree(E->d_block_count); cudaFree(E->d_perm);
+  cudaFree(E->d_split_head); cudaFree(E->d_split_alt); cudaFree(E->d_split_state); cudaFree(E->d_block_live);
   delete E;
 }
 
@@ -734,12 +797,14 @@ int mw_step(mw_engine* E, const float* actions, float* obs, int obs_stride, floa
   CK(cudaSetDevice(E->device));
   {   // launch order from the previous step's per-env cost (see k_order_*)
     int Pm = 1; while (Pm < E->n_envs && Pm < MW_SORT_MAX) Pm <<= 1;
-    int Pb = 1; while (Pb < E->n_blocks && Pb < MW_SORT_MAX) Pb <<= 1;
+    const int nb = E->n_split ? E->n_blocks_total : E->n_blocks;
+    int Pb = 1; while (Pb < nb && Pb < MW_SORT_MAX) Pb <<= 1;
     k_order_envs<<<E->n_sorted_models, 1024, sizeof(unsigned long long) * Pm, (cudaStream_t)stream>>>(E->d_model_first, E->d_model_count, E->d_perm, E->d_env_cost);
-    k_order_blocks<<<1, 1024, sizeof(unsigned long long) * Pb, (cudaStream_t)stream>>>(E->n_blocks, E->d_block_start, E->d_block_count, E->d_perm, E->d_env_cost, E->order_by_cycles ? E->d_env_cycles : nullptr, E->d_block_order);
+    k_order_blocks<<<1, 1024, sizeof(unsigned long long) * Pb, (cudaStream_t)stream>>>(nb, E->d_block_start, E->d_block_count, E->d_perm, E->d_env_cost, E->order_by_cycles ? E->d_env_cycles : nullptr, E->d_block_order,
+        E->n_blocks, E->n_split, E->d_split_head, E->d_split_alt, E->d_split_state, E->n_split ? E->d_block_live : nullptr, E->split_frac, E->n_sm);
   }
-  k_step<<<E->n_blocks, BLOCK_THREADS, smem_bytes(), (cudaStream_t)stream>>>(E->dev(), E->d_block_order, E->d_block_model, E->d_block_start, E->d_block_count, E->d_perm,
-      actions, obs, obs_stride, reward, terminated, truncated, info, info_stride, final_obs, final_info, next_snapshot);
+  k_step<<<E->n_split ? E->n_blocks_total : E->n_blocks, BLOCK_THREADS, smem_bytes(), (cudaStream_t)stream>>>(E->dev(), E->d_block_order, E->d_block_model, E->d_block_start, E->d_block_count, E->d_perm,
+      actions, obs, obs_stride, reward, terminated, truncated, info, info_stride, final_obs, final_info, next_snapshot, E->n_split ? E->d_block_live : nullptr);
   CK(cudaGetLastError());
   E->launches += 3; E->env_steps += (unsigned long long)E->n_envs;
   return MW_OK;

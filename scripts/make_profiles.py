@@ -4,7 +4,7 @@ R = sys.argv[1] if len(sys.argv) > 1 else "r01"
 G, P = "gpurun_out", "profiles"
 os.makedirs(P, exist_ok=True)
 
-def jl(path): return json.load(open(path))
+def jl(path): return json.loads(open(path).read().strip().split("\n")[-1])     # (a library banner may precede the JSON line)
 
 # 1. bench lines (one per BASELINE config that fits one GPU, + both arms of the headline, + the driver's 20-step window)
 for src, dst in (("bench_mt50.json", f"{R}_bench_mt50.json"), ("bench_ref.json", f"{R}_bench_reference.json"),
