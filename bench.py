@@ -448,8 +448,11 @@ def run_ours(args):
                            "build": lib().mw_build_info().decode(), "sharding": "env-parallel, no collective on the step path"
                                     + ("; NCCL all_gather_into_tensor of obs + packed reward/info/flags on a side stream (--gather)" if gather else ""),
                            "reference_arm": CPU_ARM_NOTE, "setup_s": round(setup_s, 1), **extra},
-                "e2e": {"value": e2e_val, "unit": "env_steps/s", "h2d_bytes_per_step": int(N * 4 * 4 + N * 4),
-                        "d2h_bytes_per_step": int(N * (obs_dim + 9) * 4), "steps": Ke, "autoresets": n_final},
+                # copies MetaWorldVecEnv.step makes per call: H2D actions [N, 4] f32 (+ the ids of the envs about to truncate, 8 B
+                # each); D2H the 39 observation columns the kernel writes (the constant one-hot columns never cross the bus), the
+                # packed [N, 9] reward / info / flags record, and the terminal rows (39 + 8 floats) of the finished envs
+                "e2e": {"value": e2e_val, "unit": "env_steps/s", "h2d_bytes_per_step": int(N * 4 * 4 + 8 * n_final / max(1, Ke)),
+                        "d2h_bytes_per_step": int(N * (39 + 9) * 4 + (39 + 8) * 4 * n_final / max(1, Ke)), "steps": Ke, "autoresets": n_final},
                 "gpu_launches": 3 * K,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": ncu.get("dram_bytes_per_launch"), "traffic_source": ncu.get("source"),
