@@ -725,3 +725,24 @@ def test_contact_overflow_path_is_bitwise_identical(torch_cuda, tmp_path):
     a, b = outs
     assert "shared 48" in a["build"] and "shared 6" in b["build"]
     assert a["steps"] == b["steps"] and a["state"] == b["state"] and a["dropped"] == b["dropped"] == 0
+
+
+def test_head_split_is_pure_scheduling(torch_cuda, tmp_path):
+    """MW_B200_SPLIT_FRAC (k_order_blocks): a model's first CTA - its seven heaviest envs - is replaced, per step and per model,
+    by two CTAs of 4 + 3 warps while its predicted duration exceeds that fraction of the balanced SM load.  Which CTA an env
+    runs in must not show in any output: per-step digests of obs / reward / info of an MT50 @ 4096 rollout (150 lock-step
+    steps: late enough for the peg-unplug / box-close heads to be split) and the final device state equal the unsplit run's."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for name, frac in (("off", None), ("split", "0.85")):
+        env = dict(os.environ)
+        env.pop("MW_B200_LIB", None); env.pop("MW_B200_SPLIT_FRAC", None)
+        if frac:
+            env["MW_B200_SPLIT_FRAC"] = frac
+        out = str(tmp_path / f"{name}.json")
+        r = subprocess.run([sys.executable, os.path.join(root, "scripts", "gpu_ab.py"), out], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs.append(json.load(open(out)))
+    a, b = outs
+    assert a["steps"] == b["steps"] and a["state"] == b["state"] and a["dropped"] == b["dropped"] == 0
