@@ -416,9 +416,16 @@ def run_ours(args):
         sys.stderr.write(f"[bench] rank {rank} on cuda:{local}: {ms / K:.4f} ms per step (device), e2e {e2e_s * 1e3 / Ke:.4f} ms, "
                          f"own work {(prof['step'] - prof['barrier_wait']) / max(1, N * min(K, 20)):.0f} cycles per env step, "
                          f"convex pairs {prof['n_convex_pairs'] / max(1, N * min(K, 20)):.3f}\n")
+    per_rank = None
     if world > 1:
         if dist.get_backend() == "gloo":
             t = t.cpu()
+        try:        # every rank's own device time, for the line (the value itself is max-over-ranks, below)
+            allt = torch.empty(world * 2, device=t.device, dtype=torch.float64)
+            dist.all_gather_into_tensor(allt, t)
+            per_rank = [round(float(x) / K, 4) for x in allt.view(world, 2)[:, 0].cpu()]
+        except Exception:
+            per_rank = None
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(t[0]), float(t[1])
     if rank == 0:
@@ -454,6 +461,9 @@ def run_ours(args):
                 "e2e": {"value": e2e_val, "unit": "env_steps/s", "h2d_bytes_per_step": int(N * 4 * 4 + 8 * n_final / max(1, Ke)),
                         "d2h_bytes_per_step": int(N * (39 + 9) * 4 + (39 + 8) * 4 * n_final / max(1, Ke)), "steps": Ke, "autoresets": n_final},
                 "gpu_launches": 3 * K,
+                **({"per_rank_ms_per_step": per_rank, "per_rank_note": "device time of every rank's own K steps; `ms_per_step` / `value` use the max.  Ranks draw "
+                    "their own task-selection / action streams, so the spread is the sample-to-sample spread of the launch's tail "
+                    "(profiles/r02_summary.md, Multi-GPU), not communication: the step path has no collective"} if per_rank else {}),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": ncu.get("dram_bytes_per_launch"), "traffic_source": ncu.get("source"),
                              "algorithmic_bytes_per_launch": bytes_step * N, "algorithmic_bytes_per_env_step": bytes_step,
