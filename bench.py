@@ -357,6 +357,7 @@ def run_ours(args):
     gen = torch.Generator(device=dev); gen.manual_seed(args.seed + rank)
     actions = torch.rand(K + W, N, 4, device=dev, generator=gen) * 2 - 1      # resident in HBM before timing
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)                    # > 126 MB L2
+    noflush = os.environ.get("MW_BENCH_NOFLUSH") == "1"        # diagnosis only (how much of a sample's tail is cold-L2 latency); the line says so
     gather = None
     if args.gather and world > 1:
         side = torch.cuda.Stream(device=dev)
@@ -376,7 +377,8 @@ def run_ours(args):
         torch.cuda.profiler.start()
     sampler.begin()
     for i in range(K):
-        flush.fill_(float(i))                       # evict L2 between timed iterations (outside the event pair)
+        if not noflush:
+            flush.fill_(float(i))                   # evict L2 between timed iterations (outside the event pair)
         ev[i][0].record()
         o, r, te, tr, inf = env.step_torch(actions[W + i])
         if gather is not None:
@@ -415,7 +417,7 @@ def run_ours(args):
     if world > 1 or "MW_BENCH_FAKE_RANK" in os.environ:
         sys.stderr.write(f"[bench] rank {rank} on cuda:{local}: {ms / K:.4f} ms per step (device), e2e {e2e_s * 1e3 / Ke:.4f} ms, "
                          f"own work {(prof['step'] - prof['barrier_wait']) / max(1, N * min(K, 20)):.0f} cycles per env step, "
-                         f"convex pairs {prof['n_convex_pairs'] / max(1, N * min(K, 20)):.3f}\n")
+                         f"convex pairs {prof['n_convex_pairs'] / max(1, N * min(K, 20)):.3f}{' NOFLUSH' if noflush else ''}\n")
     per_rank = None
     if world > 1:
         if dist.get_backend() == "gloo":
@@ -451,7 +453,8 @@ def run_ours(args):
                            "episode_phase": {"distribution": "uniform 0..499 (permuted over envs)", "min": int(phases.min()), "max": int(phases.max()),
                                              "mean": float(phases.mean()), "autoresets_in_timed_region": n_autoreset,
                                              "expected_autoresets": N * K / 500.0, "pre_roll_steps": 500},
-                           "l2": "256 MB device write between timed steps (outside the per-step CUDA-event pairs)",
+                           "l2": ("NO L2 FLUSH (MW_BENCH_NOFLUSH=1): a diagnosis run, not a benchmark value" if noflush else
+                                  "256 MB device write between timed steps (outside the per-step CUDA-event pairs)"),
                            "build": lib().mw_build_info().decode(), "sharding": "env-parallel, no collective on the step path"
                                     + ("; NCCL all_gather_into_tensor of obs + packed reward/info/flags on a side stream (--gather)" if gather else ""),
                            "reference_arm": CPU_ARM_NOTE, "setup_s": round(setup_s, 1), **extra},

@@ -1,3 +1,3 @@
-mkdir -p gpurun_out
-timeout 60 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout 100 python -m pytest tests/test_gpu.py -q -x -p no:cacheprovider -k "heterogeneous or determinis or mt10_full_size or resume" 2>&1 | tail -3
+A="--steps 30 --warmup 3 --e2e-steps 3 --cpu-steps-per-env 1"
+(MW_BENCH_NOFLUSH=1 MW_BENCH_FAKE_RANK=1 timeout 60 python bench.py $A > /dev/null 2> /tmp/r1.err; grep '\[bench\]' /tmp/r1.err | cut -c1-150) &
+wait
